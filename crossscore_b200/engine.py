@@ -1,0 +1,354 @@
+"""Host-side plan of the CrossScore forward: packed weights + the kernel sequence over the C ABI.
+
+PyTorch is used for device memory (torch.empty), streams and the one-off weight re-layout; every
+operation of the forward itself is a call into libcrossscore_sm100a.so (crossscore_b200._lib).
+
+Data layout in HBM (C = 384, P = patches/image, T = P + 1, I = images in the batch, AT = bf16 | fp32):
+  h      (I*T, C)   fp32   DINOv2 residual stream (kept fp32: outlier channels)
+  y      (I*T, C)   AT     LayerNorm output = GEMM A operand
+  qkv    (I*T, 3C)  AT     fused Q|K|V projection, head h at columns h*64 of each part
+  att    (I*T, C)   AT     attention output, heads concatenated
+  g      (I*T, 4C)  AT     MLP hidden (GELU fused in the fc1 epilogue)
+  xq32/xq (B*P, C)  fp32/AT  decoder stream (post-norm: fp32 copy is the residual, AT copy feeds GEMMs)
+  mem    (B*N*P, C) AT     reference tokens (+PE); layer-invariant, so K/V of BOTH decoder layers come
+                           from ONE GEMM:  kv (B*N*P, 2 layers x (K|V) x 8 heads x slot)
+  decoder heads are 48 wide; the bf16 path stores them in 64-column slots (weights zero-padded) so the
+  attention kernel's TMA boxes are 128 bytes; QK^T runs 3 K-steps and PV runs N=48, no padded FLOPs.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, call
+
+C = 384
+PATCH = 14
+DINO_HEADS, DINO_LAYERS, DINO_EPS = 6, 12, 1e-6
+DEC_HEADS, DEC_LAYERS, DEC_EPS, DEC_D = 8, 2, 1e-5, 48
+NUM_SMS_HINT = 148
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class PackedWeights:
+    """Kernel-friendly copies of the reference state_dict (built once per device / precision)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device, precision: str, do_self_attn: bool = True):
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.dt = DT_BF16 if precision == "bf16" else DT_F32
+        self.wdtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.slot = 64 if precision == "bf16" else DEC_D  # decoder head slot width
+        self.device = device
+        f32 = lambda k: sd[k].detach().to(device=device, dtype=torch.float32).contiguous()
+        W = lambda t: t.to(self.wdtype).contiguous()
+        b = "backbone."
+        # --- patch embed: Conv2d weight (384,3,14,14) -> (384, 588) [c, ky, kx], K zero-padded to 592 for TMA
+        wpe = f32(b + "embeddings.patch_embeddings.projection.weight").reshape(C, 588)
+        if precision == "bf16":
+            wpe = torch.nn.functional.pad(wpe, (0, 4))
+        self.w_pe, self.b_pe = W(wpe), f32(b + "embeddings.patch_embeddings.projection.bias")
+        self.cls = f32(b + "embeddings.cls_token").reshape(C)
+        self.pos = f32(b + "embeddings.position_embeddings")[0].contiguous()  # (1+37*37, C)
+        self.layers = []
+        for l in range(DINO_LAYERS):
+            p = f"{b}encoder.layer.{l}."
+            lam1, lam2 = f32(p + "layer_scale1.lambda1"), f32(p + "layer_scale2.lambda1")
+            L = dict(
+                ln1_g=f32(p + "norm1.weight"), ln1_b=f32(p + "norm1.bias"),
+                wqkv=W(torch.cat([f32(p + "attention.attention.query.weight"),
+                                  f32(p + "attention.attention.key.weight"),
+                                  f32(p + "attention.attention.value.weight")], 0)),
+                bqkv=torch.cat([f32(p + "attention.attention.query.bias"), f32(p + "attention.attention.key.bias"),
+                                f32(p + "attention.attention.value.bias")], 0).contiguous(),
+                # LayerScale folded into the producing Linear in fp32, before any rounding:
+                #   h += lam * (a W^T + b)  ==  h += a (lam*W)^T + lam*b
+                wo=W(f32(p + "attention.output.dense.weight") * lam1[:, None]),
+                bo=(f32(p + "attention.output.dense.bias") * lam1).contiguous(),
+                ln2_g=f32(p + "norm2.weight"), ln2_b=f32(p + "norm2.bias"),
+                w1=W(f32(p + "mlp.fc1.weight")), b1=f32(p + "mlp.fc1.bias"),
+                w2=W(f32(p + "mlp.fc2.weight") * lam2[:, None]), b2=(f32(p + "mlp.fc2.bias") * lam2).contiguous(),
+            )
+            self.layers.append(L)
+        self.lnf_g, self.lnf_b = f32(b + "layernorm.weight"), f32(b + "layernorm.bias")
+        self.pe_table = f32("pos_enc_fn.PE")[0].contiguous()  # (pe_h, pe_w, C)
+
+        # --- decoder: per-head 48 -> slot padding of the packed in-proj rows
+        slot, E = self.slot, DEC_HEADS * self.slot
+
+        def pad_heads(w):  # (8*48, X) -> (8*slot, X)
+            if slot == DEC_D:
+                return w
+            w = w.reshape(DEC_HEADS, DEC_D, -1)
+            out = torch.zeros(DEC_HEADS, slot, w.shape[-1], device=w.device, dtype=w.dtype)
+            out[:, :DEC_D] = w
+            return out.reshape(DEC_HEADS * slot, -1)
+
+        def pad_heads_b(bv):
+            return pad_heads(bv[:, None])[:, 0]
+
+        self.dec = []
+        kv_w, kv_b = [], []
+        for l in range(DEC_LAYERS):
+            p = f"ref_cross.attn.layers.{l}."
+            D = {}
+            if do_self_attn:
+                wi, bi = f32(p + "self_attn.in_proj_weight"), f32(p + "self_attn.in_proj_bias")
+                D["sa_win"] = W(torch.cat([pad_heads(wi[i * C:(i + 1) * C]) for i in range(3)], 0))
+                D["sa_bin"] = torch.cat([pad_heads_b(bi[i * C:(i + 1) * C]) for i in range(3)], 0).contiguous()
+                D["sa_wo"], D["sa_bo"] = W(f32(p + "self_attn.out_proj.weight")), f32(p + "self_attn.out_proj.bias")
+            wi, bi = f32(p + "multihead_attn.in_proj_weight"), f32(p + "multihead_attn.in_proj_bias")
+            D["ca_wq"], D["ca_bq"] = W(pad_heads(wi[:C])), pad_heads_b(bi[:C]).contiguous()
+            kv_w += [pad_heads(wi[C:2 * C]), pad_heads(wi[2 * C:])]
+            kv_b += [pad_heads_b(bi[C:2 * C]), pad_heads_b(bi[2 * C:])]
+            D["ca_wo"], D["ca_bo"] = W(f32(p + "multihead_attn.out_proj.weight")), f32(p + "multihead_attn.out_proj.bias")
+            D["w1"], D["b1"] = W(f32(p + "linear1.weight")), f32(p + "linear1.bias")
+            D["w2"], D["b2"] = W(f32(p + "linear2.weight")), f32(p + "linear2.bias")
+            for n in (1, 2, 3):
+                D[f"ln{n}_g"], D[f"ln{n}_b"] = f32(p + f"norm{n}.weight"), f32(p + f"norm{n}.bias")
+            self.dec.append(D)
+        # K/V projection of BOTH layers as one weight: rows [l*2E, l*2E+E) = K_l, [l*2E+E, (l+1)*2E) = V_l
+        self.kv_w, self.kv_b = W(torch.cat(kv_w, 0)), torch.cat(kv_b, 0).contiguous()
+        self.E = E
+        # --- head
+        self.h0_w, self.h0_b = W(f32("ref_cross.head.0.weight")), f32("ref_cross.head.0.bias")
+        h2w, h2b = f32("ref_cross.head.2.weight"), f32("ref_cross.head.2.bias")
+        if precision == "bf16":  # rows padded 196 -> 224 (one tcgen05 N tile)
+            h2w = torch.nn.functional.pad(h2w, (0, 0, 0, 28))
+            h2b = torch.nn.functional.pad(h2b, (0, 28))
+        self.h2_w, self.h2_b = W(h2w), h2b.contiguous()
+        self._tables = {}
+
+    # resampled tables are cached per patch grid
+    def tables(self, ph: int, pw: int, stream):
+        key = (ph, pw)
+        if key not in self._tables:
+            dev = self.device
+            g = int(round(math.sqrt(self.pos.shape[0] - 1)))
+            if ph == g and pw == g:  # modeling_dinov2.py:71-72: table used as is
+                pos = self.pos
+            else:
+                pos = torch.empty(1 + ph * pw, C, device=dev, dtype=torch.float32)
+                pos[0] = self.pos[0]
+                call("xs_pos_embed_resample_bicubic", _ptr(self.pos[1:]), _ptr(pos[1:]), g, g, ph, pw, C, stream)
+            pe_h, pe_w = self.pe_table.shape[:2]
+            if ph == pe_h and pw == pe_w:  # positional_encoding.py:51-56 shortcut
+                pe = self.pe_table.reshape(ph * pw, C)
+            else:
+                pe = torch.empty(ph * pw, C, device=dev, dtype=torch.float32)
+                call("xs_pe_resample_bilinear_ac", _ptr(self.pe_table), _ptr(pe), pe_h, pe_w, ph, pw, C, stream)
+            self._tables[key] = (pos, pe)
+        return self._tables[key]
+
+
+class Engine:
+    """Runs the forward on one GPU.  One Engine per (module, device, precision)."""
+
+    def __init__(self, sd, device, precision="bf16", do_self_attn=True, do_short_cut=True,
+                 use_tanh=False, power=1.0):
+        _lib.load()
+        with torch.cuda.device(device):
+            call("xs_device_check")
+        self.w = PackedWeights(sd, device, precision, do_self_attn)
+        self.device = device
+        self.dt = self.w.dt
+        self.adtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.do_self_attn, self.do_short_cut = do_self_attn, do_short_cut
+        self.use_tanh, self.power = bool(use_tanh), float(power)
+        self._ws = {}
+
+    # ---- scratch -----------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        key = (name, dtype)
+        cur = self._ws.get(key)
+        if cur is None or cur.numel() < n:
+            cur = torch.empty(max(n, 1), device=self.device, dtype=dtype)
+            self._ws[key] = cur
+        return cur[:n].view(*shape)
+
+    # ---- thin op wrappers ----------------------------------------------------------------------
+    def _gemm(self, A, Wt, bias, out, act, st):
+        M, K = A.shape
+        N = Wt.shape[0]
+        call("xs_gemm_bias_act", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(out), out.stride(0),
+             M, N, K, act, self.dt, st)
+        _lib.count_launch()
+
+    def _ln(self, res_in, delta, res_out, g, b, eps, y, y32, rows, st):
+        call("xs_layernorm", _ptr(res_in), _ptr(delta), _ptr(res_out), _ptr(g), _ptr(b), eps, _ptr(y), _ptr(y32),
+             rows, self.dt, st)
+        _lib.count_launch()
+
+    def _attn(self, q, k, v, o, B, heads, Lq, Lk, d, slot, q_rs, q_bs, kv_rs, kv_bs, kv_shared, st,
+              lse=None, name="att"):
+        """q/k/v are tensor views whose data_ptr is the first column of the respective part."""
+        scale = 1.0 / math.sqrt(d)
+        ctas = B * heads * ((Lq + 127) // 128)
+        nblk = (Lk + 127) // 128
+        nsplit = max(1, min((2 * NUM_SMS_HINT) // max(ctas, 1), nblk // 4))
+        per = -(-nblk // nsplit)
+        nsplit = -(-nblk // per)  # every split owns at least one key block
+        if nsplit == 1:
+            o_is_f32 = 1 if self.dt == DT_F32 else 0
+            call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, Lq, Lk, d, slot,
+                 q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), 1, o_is_f32, scale, self.dt, st)
+            _lib.count_launch()
+        else:  # small batch: split the keys across CTAs, then merge (same merge as the multi-GPU path)
+            o_parts = self._buf(name + "_oparts", (nsplit, B * Lq, heads * d), torch.float32)
+            l_parts = self._buf(name + "_lparts", (nsplit, B, heads, Lq), torch.float32)
+            call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o_parts), _ptr(l_parts), B, heads, Lq, Lk, d, slot,
+                 q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), nsplit, 1, scale, self.dt, st)
+            call("xs_lse_merge", _ptr(o_parts), _ptr(l_parts), _ptr(o), _ptr(lse), nsplit, B, Lq, heads, d, self.dt, st)
+            _lib.count_launch(2)
+
+    # ---- DINOv2 backbone over a list of image tensors (each (n,3,H,W) fp32, same H,W) --------------
+    def backbone(self, image_groups, st):
+        """Returns (h, delta, n_img, P): the fp32 residual stream BEFORE the last fc2 residual add and the
+        pending delta, so the caller fuses `h + delta -> final LN` into its own consumer kernel."""
+        w = self.w
+        H, Wd = image_groups[0].shape[-2:]
+        ph, pw = H // PATCH, Wd // PATCH
+        P, T = ph * pw, ph * pw + 1
+        I = sum(int(g.shape[0]) for g in image_groups)
+        pos, _ = w.tables(ph, pw, st)
+        A = self.adtype
+        tok = self._buf("tok", (I * P, C), A)
+        row = 0
+        for g in image_groups:
+            n = int(g.shape[0])
+            assert g.dtype == torch.float32 and g.is_contiguous() and g.shape[1] == 3
+            nbytes = _lib.load().xs_workspace_bytes(_lib.OP_PATCH_EMBED, n, H, Wd, self.dt)
+            ws = self._buf("im2col", (nbytes,), torch.uint8)
+            call("xs_patch_embed", _ptr(g), _ptr(w.w_pe), _ptr(w.b_pe), _ptr(tok[row * P:]), _ptr(ws), nbytes, n, H, Wd,
+                 self.dt, st)
+            _lib.count_launch(2)
+            row += n
+        R = I * T
+        h = self._buf("h", (R, C), torch.float32)
+        y = self._buf("y", (R, C), A)
+        qkv = self._buf("qkv", (R, 3 * C), A)
+        att = self._buf("att", (R, C), A)
+        d = self._buf("d", (R, C), A)
+        g1 = self._buf("g", (R, 4 * C), A)
+        L0 = w.layers[0]
+        call("xs_embed_cls_pos_ln", _ptr(tok), _ptr(w.cls), _ptr(pos), _ptr(h), _ptr(L0["ln1_g"]), _ptr(L0["ln1_b"]),
+             DINO_EPS, _ptr(y), I, P, self.dt, st)
+        _lib.count_launch()
+        for l, L in enumerate(w.layers):
+            self._gemm(y, L["wqkv"], L["bqkv"], qkv, ACT_NONE, st)
+            self._attn(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, I, DINO_HEADS, T, T, 64, 64,
+                       3 * C, T * 3 * C, 3 * C, T * 3 * C, False, st, name="dino")
+            self._gemm(att, L["wo"], L["bo"], d, ACT_NONE, st)
+            self._ln(h, d, h, L["ln2_g"], L["ln2_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN2(h)
+            self._gemm(y, L["w1"], L["b1"], g1, ACT_GELU, st)
+            self._gemm(g1, L["w2"], L["b2"], d, ACT_NONE, st)
+            if l + 1 < DINO_LAYERS:
+                Ln = w.layers[l + 1]
+                self._ln(h, d, h, Ln["ln1_g"], Ln["ln1_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN1_{l+1}(h)
+        return h, d, I, P
+
+    def features(self, query_img, ref_imgs, st, want_mem=True):
+        """DINOv2 + final LN + CLS drop + PE.  query_img (B,3,H,W) or None, ref_imgs (B,N,3,H,W) or None.
+        Returns xq32 (B*P,C) fp32, xq (B*P,C) AT, mem (B*N*P,C) AT (None where not requested)."""
+        w = self.w
+        groups, nq = [], 0
+        if query_img is not None:
+            groups.append(query_img)
+            nq = int(query_img.shape[0])
+        nr = 0
+        if ref_imgs is not None:
+            r = ref_imgs.reshape(-1, *ref_imgs.shape[-3:])
+            groups.append(r)
+            nr = int(r.shape[0])
+        H, Wd = groups[0].shape[-2:]
+        ph, pw = H // PATCH, Wd // PATCH
+        h, d, I, P = self.backbone(groups, st)
+        _, pe = w.tables(ph, pw, st)
+        xq32 = self._buf("xq32", (nq * P, C), torch.float32) if nq else None
+        xq = self._buf("xq", (nq * P, C), self.adtype) if nq else None
+        mem = self._buf("mem", (nr * P, C), self.adtype) if nr and want_mem else None
+        call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS, _ptr(pe),
+             _ptr(xq32), _ptr(xq), _ptr(mem), I, nq, P, self.dt, st)
+        _lib.count_launch()
+        return xq32, xq, mem
+
+    def project_kv(self, mem, st, out=None):
+        """K/V of both decoder layers for reference tokens mem (rows, C) -> (rows, 4E)."""
+        rows = mem.shape[0]
+        kv = out if out is not None else self._buf("kv", (rows, 4 * self.w.E), self.adtype)
+        self._gemm(mem, self.w.kv_w, self.w.kv_b, kv, ACT_NONE, st)
+        return kv
+
+    def decode(self, xq32, xq, kv, B, P, M, ph, pw, st, kv_shared=False, need_attn_weights=False, head_id=0,
+               cross_attn_fn=None):
+        """2-layer post-norm decoder + head + jigsaw.  kv: (B*M or M, 4E) projected reference K/V.
+        cross_attn_fn (optional) replaces the local cross-attention call (multi-GPU split-KV)."""
+        w, A, E, slot = self.w, self.adtype, self.w.E, self.w.slot
+        R = B * P
+        qkv_s = self._buf("dec_qkv", (R, 3 * E), A)
+        qc = self._buf("dec_q", (R, E), A)
+        att = self._buf("dec_att", (R, C), A)
+        d = self._buf("dec_d", (R, C), A)
+        f = self._buf("dec_f", (R, C), A)
+        lse = self._buf("dec_lse", (B, DEC_HEADS, P), torch.float32) if need_attn_weights else None
+        sc = self.do_short_cut
+        for l, D in enumerate(w.dec):
+            if self.do_self_attn:
+                self._gemm(xq, D["sa_win"], D["sa_bin"], qkv_s, ACT_NONE, st)
+                self._attn(qkv_s[:, 0:], qkv_s[:, E:], qkv_s[:, 2 * E:], att, B, DEC_HEADS, P, P, DEC_D, slot,
+                           3 * E, P * 3 * E, 3 * E, P * 3 * E, False, st, name="dsa")
+                self._gemm(att, D["sa_wo"], D["sa_bo"], d, ACT_NONE, st)
+                self._ln(xq32 if sc else None, d, None, D["ln1_g"], D["ln1_b"], DEC_EPS, xq, xq32, R, st)
+            self._gemm(xq, D["ca_wq"], D["ca_bq"], qc, ACT_NONE, st)
+            k_view, v_view = kv[:, l * 2 * E:], kv[:, l * 2 * E + E:]
+            last = need_attn_weights and l == DEC_LAYERS - 1
+            if cross_attn_fn is not None:
+                cross_attn_fn(l, qc, att, lse if last else None, st)
+            else:
+                self._attn(qc, k_view, v_view, att, B, DEC_HEADS, P, M, DEC_D, slot, E, P * E, 4 * E, M * 4 * E,
+                           kv_shared, st, lse=lse if last else None, name="dca")
+            self._gemm(att, D["ca_wo"], D["ca_bo"], d, ACT_NONE, st)
+            self._ln(xq32 if sc else None, d, None, D["ln2_g"], D["ln2_b"], DEC_EPS, xq, xq32, R, st)
+            self._gemm(xq, D["w1"], D["b1"], f, ACT_RELU, st)
+            self._gemm(f, D["w2"], D["b2"], d, ACT_NONE, st)
+            self._ln(xq32, d, None, D["ln3_g"], D["ln3_b"], DEC_EPS, xq, xq32, R, st)
+        probs = None
+        if need_attn_weights:
+            if not 0 <= head_id < DEC_HEADS:
+                raise IndexError(f"need_attn_weights_head_id={head_id} out of range for {DEC_HEADS} heads")
+            probs = torch.empty(B, P, M, device=self.device, dtype=torch.float32)
+            l = DEC_LAYERS - 1
+            call("xs_attn_probs_one_head", _ptr(qc), _ptr(kv[:, l * 2 * E:]), _ptr(lse), _ptr(probs), B, DEC_HEADS,
+                 head_id, P, M, DEC_D, slot, E, P * E, 4 * E, 0 if kv_shared else M * 4 * E, 1.0 / math.sqrt(DEC_D),
+                 self.dt, st)
+            _lib.count_launch()
+        self._gemm(xq, w.h0_w, w.h0_b, f, ACT_LEAKY, st)
+        score = torch.empty(B, PATCH * ph, PATCH * pw, device=self.device, dtype=torch.float32)
+        call("xs_head_score_jigsaw", _ptr(f), f.stride(0), _ptr(w.h2_w), w.h2_w.stride(0), _ptr(w.h2_b), _ptr(score), B,
+             ph, pw, C, int(self.use_tanh), self.power, self.dt, st)
+        _lib.count_launch()
+        return score, probs
+
+    # ---- the reference-shaped forward ------------------------------------------------------------
+    def forward(self, query_img, ref_imgs, need_attn_weights=False, head_id=0):
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        B, _, H, Wd = query_img.shape
+        N = ref_imgs.shape[1]
+        ph, pw = H // PATCH, Wd // PATCH
+        P = ph * pw
+        xq32, xq, mem = self.features(query_img, ref_imgs, st)
+        kv = self.project_kv(mem, st)
+        score, probs = self.decode(xq32, xq, kv, B, P, N * P, ph, pw, st, kv_shared=False,
+                                   need_attn_weights=need_attn_weights, head_id=head_id)
+        if probs is not None:
+            probs = probs.view(B, ph, pw, N, ph, pw)
+        return score, probs

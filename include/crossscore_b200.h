@@ -1,0 +1,127 @@
+/* crossscore_b200 -- C ABI of the B200 (sm_100a) CrossScore inference hot path.
+ *
+ * The reference (ActiveVisionLab/CrossScore) has no FFI: the path sits behind a PyTorch nn.Module
+ * (task/core.py:26-161, CrossScoreNet) whose arithmetic is torch / HF-transformers library calls.
+ * This header is the boundary a maintainer binds instead of those calls (ctypes stub in INTEGRATION.md):
+ * one entry per fused operator, plain pointers and sizes, no torch types.  Each entry cites the
+ * reference call site(s) it replaces (paths relative to the reference root; $SP = site-packages of the
+ * reference's pinned torch / transformers).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument / unsupported shape, >0 a cudaError_t value;
+ *     xs_last_error() returns the message of the last failure on the calling thread.  Nothing throws
+ *     or exits.
+ *   - all pointers are DEVICE pointers on the current CUDA device, 16-byte aligned; the caller owns all
+ *     memory (PyTorch caching allocator in the shipped host code); kernels are enqueued on `stream`
+ *     (a cudaStream_t) with no implicit synchronisation and are CUDA-graph capturable.
+ *   - dtype selects the activation storage: XS_DTYPE_BF16 (tcgen05 tensor-core path) or
+ *     XS_DTYPE_F32 (fp32 parity mode, SIMT).  Statistics, residual stream, tables, biases and the score
+ *     map are always fp32.  Hidden size is 384 (DINOv2-small) throughout.
+ *   - bf16 attention operands use 64-column head slots: head h of a row lives at columns
+ *     [h*64, h*64+head_dim); for head_dim 48 (decoder) the projection weights are padded so the 16
+ *     trailing columns of each slot are never read.
+ */
+#ifndef CROSSSCORE_B200_H_
+#define CROSSSCORE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XS_ABI_VERSION 1
+
+#define XS_DTYPE_BF16 0
+#define XS_DTYPE_F32 1
+
+#define XS_ACT_NONE 0
+#define XS_ACT_GELU 1  /* exact (erf) GELU: Dinov2MLP, $SP/transformers/models/dinov2/modeling_dinov2.py:312-328 */
+#define XS_ACT_RELU 2  /* decoder FFN: model/customised_transformer/transformer.py:59,208-210 */
+#define XS_ACT_LEAKY 3 /* head LeakyReLU(0.01): model/cross_reference.py:47 */
+
+#define XS_OP_PATCH_EMBED 1
+
+typedef void* xs_stream_t; /* cudaStream_t */
+
+int xs_version(void);
+const char* xs_last_error(void);
+/* 0 if the current device is compute capability 10.x (B200), <0 otherwise */
+int xs_device_check(void);
+/* scratch bytes an operator needs; XS_OP_PATCH_EMBED: (n_images, H, W) */
+size_t xs_workspace_bytes(int op, int a, int b, int c, int dtype);
+
+/* K1  Dinov2PatchEmbeddings.projection: Conv2d(3,384,k=14,s=14) == im2col + GEMM
+ *     ($SP/transformers/models/dinov2/modeling_dinov2.py:139-149).
+ *     img (I,3,H,W) fp32;  w: bf16 (384,592) zero-padded K / fp32 (384,588);  tok (I*P,384). */
+int xs_patch_embed(const float* img, const void* w, const float* bias, void* tok, void* workspace,
+                   size_t workspace_bytes, int n_images, int H, int W, int dtype, xs_stream_t stream);
+
+/* K1b CLS cat + position embedding add (modeling_dinov2.py:108-112) fused with layer-0 norm1 (:354,371).
+ *     h (I*(P+1),384) fp32 residual stream out;  y = LN(h) in activation dtype. */
+int xs_embed_cls_pos_ln(const void* tok, const float* cls, const float* pos, float* h, const float* gamma,
+                        const float* beta, float eps, void* y, int n_images, int P, int dtype,
+                        xs_stream_t stream);
+
+/* K2  LayerNorm with fused residual add: x = res_in + delta;  res_out = x (optional);
+ *     y = LN(x) (activation dtype, optional);  y32 = LN(x) (fp32, optional).
+ *     DINOv2 pre-norm: modeling_dinov2.py:354,359,371-384;  decoder post-norm:
+ *     model/customised_transformer/transformer.py:157-173.  res_in or delta may be NULL. */
+int xs_layernorm(const float* res_in, const void* delta, float* res_out, const float* gamma, const float* beta,
+                 float eps, void* y, float* y32, int rows, int dtype, xs_stream_t stream);
+
+/* K8  final DINOv2 LayerNorm (modeling_dinov2.py:477) + CLS drop + query/reference split
+ *     (task/core.py:142-153) + multi-view PE add (model/positional_encoding.py:72-74).
+ *     Images are ordered "all queries, then references (b, n)": images [0,n_query_images) ->
+ *     xq32 / xq (n_query*P, 384), images [n_query_images, n_images) -> mem ((n_images-n_query)*P, 384).
+ *     xq32, xq, mem may each be NULL. */
+int xs_final_ln_drop_cls_add_pe(const float* h, const void* delta, const float* gamma, const float* beta,
+                                float eps, const float* pe, float* xq32, void* xq, void* mem, int n_images,
+                                int n_query_images, int P, int dtype, xs_stream_t stream);
+
+/* PE table (ih,iw,C) -> (oh,ow,C), bilinear align_corners=True (model/positional_encoding.py:61-69) */
+int xs_pe_resample_bilinear_ac(const float* table, float* out, int ih, int iw, int oh, int ow, int channels,
+                               xs_stream_t stream);
+/* DINOv2 pos-emb grid (ih,iw,C) -> (oh,ow,C), bicubic align_corners=False (modeling_dinov2.py:57-95) */
+int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw, int oh, int ow, int channels,
+                                  xs_stream_t stream);
+
+/* K3,K5-K7,K9-K11  out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N])   (torch.nn.Linear everywhere on the path)
+ *     bf16: N multiple of 192 or 256, K/lda/ldw/ldc multiples of 8.  fp32: any shape, lda/ldw % 4 == 0. */
+int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc,
+                     int M, int N, int K, int act, int dtype, xs_stream_t stream);
+
+/* K4,K9,K10  O = softmax(Q K^T * scale) V  per (batch, head), no mask
+ *     (modeling_dinov2.py:203-234; $SP/torch/nn/functional.py:6630-6692 via transformer.py:182-205).
+ *     head_slot: column pitch between heads in q/k/v rows (bf16: must be 64).  kv_shared: all batches
+ *     read batch 0 of k/v (scene-level reference cache).  nsplit > 1: o is the fp32 partial buffer
+ *     [nsplit][B*Lq][heads*head_dim] and lse [nsplit][B][heads][Lq] must be given (merge with xs_lse_merge).
+ *     lse (optional for nsplit == 1) = ln sum_j exp(scale * q.k_j). */
+int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq,
+                  int Lk, int head_dim, int head_slot, long long q_row_stride, long long q_batch_stride,
+                  long long kv_row_stride, long long kv_batch_stride, int kv_shared, int nsplit, int o_is_f32,
+                  float scale, int dtype, xs_stream_t stream);
+
+/* C2  split-KV merge: LSE = log sum_r exp(LSE_r), O = sum_r exp(LSE_r - LSE) O_r  (no reference counterpart;
+ *     identity in SURVEY.md appendix B-10).  Parts may come from local splits or an NCCL all-gather. */
+int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float* lse_out, int n_parts, int B,
+                 int Lq, int heads, int head_dim, int dtype, xs_stream_t stream);
+
+/* K12  head[2] Linear(384->196) + Sigmoid/Tanh (+pow) + jigsaw_to_image
+ *      (model/cross_reference.py:45-50,82-87; model/regression_layer.py:26-62; utils/misc/image.py:8-21).
+ *      A (B*ph*pw, 384);  W: bf16 (224,384) zero-padded rows / fp32 (196,384);  score (B,14ph,14pw) fp32. */
+int xs_head_score_jigsaw(const void* A, int lda, const void* W, int ldw, const float* bias, float* score, int B,
+                         int ph, int pw, int K, int use_tanh, float power, int dtype, xs_stream_t stream);
+
+/* K13  attention probabilities of one head (need_attn_weights=True; transformer.py:175-178,
+ *      cross_reference.py:91-93): probs[b,i,j] = exp(scale * q_i.k_j - lse[b,head,i]),  (B,Lq,Lk) fp32 */
+int xs_attn_probs_one_head(const void* q, const void* k, const float* lse, float* probs, int B, int heads,
+                           int head, int Lq, int Lk, int head_dim, int head_slot, long long q_row_stride,
+                           long long q_batch_stride, long long kv_row_stride, long long kv_batch_stride,
+                           float scale, int dtype, xs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROSSSCORE_B200_H_ */

@@ -1,0 +1,297 @@
+"""Per-kernel parity tests on the B200, through the C ABI (crossscore_b200._lib).
+
+Each CUDA entry point is compared with a plain PyTorch fp32/fp64 restatement of the same operator on the
+same seeded inputs (for the fp32 parity mode: tight tolerances; for the bf16 tensor-core path: bf16
+round-off of operands/outputs).  Ragged sizes (M, L not multiples of the tile) are the default here
+because the real shapes are ragged (T = 1370, P = 1369, M = 6845).
+"""
+import math
+
+import pytest
+import torch
+
+from crossscore_b200 import _lib
+from crossscore_b200._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, call
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def act_ref(x, act):
+    if act == ACT_GELU:
+        return 0.5 * x * (1 + torch.erf(x / math.sqrt(2)))
+    if act == ACT_RELU:
+        return torch.relu(x)
+    if act == ACT_LEAKY:
+        return torch.where(x >= 0, x, 0.01 * x)
+    return x
+
+
+def test_library_and_device():
+    lib = _lib.load()
+    assert lib.xs_version() == 1
+    call("xs_device_check")
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,act", [(300, 384, 384, ACT_NONE), (1000, 1152, 384, ACT_GELU), (77, 196, 588, ACT_RELU),
+                                       (513, 384, 1536, ACT_LEAKY)])
+def test_gemm_f32(M, N, K, act):
+    A, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    out = torch.empty(M, N, device=DEV)
+    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_F32, st())
+    ref = act_ref(A.double() @ W.double().T + b.double(), act)
+    assert (out.double() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,act", [
+    (128, 192, 64, ACT_NONE),       # one tile, one k-block
+    (128, 384, 384, ACT_NONE),      # BN=192 x2
+    (300, 384, 384, ACT_NONE),      # M tail
+    (1000, 1152, 384, ACT_GELU),    # qkv-like / gelu
+    (1370 * 3, 1536, 384, ACT_GELU),
+    (1369, 384, 592, ACT_NONE),     # patch-embed K (zero-filled K tail block)
+    (777, 384, 1536, ACT_NONE),     # fc2 K
+    (1369, 2048, 384, ACT_NONE),    # BN=256
+    (1369, 512, 384, ACT_RELU),
+    (40000, 384, 384, ACT_LEAKY),   # many tiles per CTA (persistent loop, phase wrap)
+])
+def test_gemm_bf16_tc(M, N, K, act):
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+    b = rnd(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_BF16, st())
+    torch.cuda.synchronize()
+    ref = act_ref(A.float() @ W.float().T + b, act)
+    err = (out.float() - ref).abs()
+    tol = 0.02 + 0.01 * ref.abs()
+    assert torch.isfinite(out.float()).all()
+    assert (err <= tol).all(), f"max err {err.max().item()} at {err.argmax().item()}"
+    assert err.mean() < 5e-3
+
+
+def test_gemm_bf16_rejects_bad_shapes():
+    A = rnd(128, 384, dtype=torch.bfloat16)
+    W = rnd(200, 384, dtype=torch.bfloat16)
+    b = rnd(200)
+    out = torch.empty(128, 200, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.XsError):
+        call("xs_gemm_bias_act", P(A), 384, P(W), 384, P(b), P(out), 200, 128, 200, 384, ACT_NONE, DT_BF16, st())
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attn_ref(q, k, v, scale):
+    # q (B,H,Lq,d), k/v (B,H,Lk,d) double
+    s = (q @ k.transpose(-1, -2)) * scale
+    lse = torch.logsumexp(s, -1)
+    return torch.softmax(s, -1) @ v, lse
+
+
+def run_attn(dtype_flag, B, H, Lq, Lk, d, slot, nsplit=1, kv_shared=False, seed=0, qscale=1.0):
+    adt = torch.bfloat16 if dtype_flag == DT_BF16 else torch.float32
+    Bkv = 1 if kv_shared else B
+    q = rnd(B, Lq, H * slot, seed=seed, scale=qscale, dtype=adt)
+    k = rnd(Bkv, Lk, H * slot, seed=seed + 1, dtype=adt)
+    v = rnd(Bkv, Lk, H * slot, seed=seed + 2, dtype=adt)
+    scale = 1.0 / math.sqrt(d)
+    o_f32 = 1 if (dtype_flag == DT_F32 or nsplit > 1) else 0
+    o = torch.full((nsplit, B * Lq, H * d), float("nan"), device=DEV, dtype=torch.float32 if o_f32 else adt)
+    lse = torch.full((nsplit, B, H, Lq), float("nan"), device=DEV)
+    call("xs_flash_attn", P(q), P(k), P(v), P(o), P(lse), B, H, Lq, Lk, d, slot, H * slot, Lq * H * slot, H * slot,
+         Lk * H * slot, int(kv_shared), nsplit, o_f32, scale, dtype_flag, st())
+    if nsplit > 1:
+        merged = torch.empty(B * Lq, H * d, device=DEV, dtype=adt)
+        lse_m = torch.empty(B, H, Lq, device=DEV)
+        call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d, dtype_flag, st())
+        o, lse = merged, lse_m
+    else:
+        o, lse = o[0], lse[0]
+    torch.cuda.synchronize()
+    qd = q.double().view(B, Lq, H, slot)[..., :d].transpose(1, 2)
+    kd = k.double().view(Bkv, Lk, H, slot)[..., :d].transpose(1, 2).expand(B, -1, -1, -1)
+    vd = v.double().view(Bkv, Lk, H, slot)[..., :d].transpose(1, 2).expand(B, -1, -1, -1)
+    ref, lse_ref = attn_ref(qd, kd, vd, scale)
+    ref = ref.transpose(1, 2).reshape(B * Lq, H * d)
+    return o.double(), ref, lse.double(), lse_ref
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d,slot,nsplit,shared", [
+    (2, 6, 150, 150, 64, 64, 1, False),
+    (1, 8, 130, 333, 48, 48, 1, False),
+    (2, 8, 70, 1000, 48, 48, 3, False),
+    (3, 8, 65, 200, 48, 48, 1, True),
+])
+def test_flash_attn_f32(B, H, Lq, Lk, d, slot, nsplit, shared):
+    o, ref, lse, lse_ref = run_attn(DT_F32, B, H, Lq, Lk, d, slot, nsplit, shared)
+    assert (o - ref).abs().max() < 2e-5
+    assert (lse - lse_ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d,nsplit,shared,qscale", [
+    (1, 1, 128, 128, 64, 1, False, 1.0),     # single tile
+    (1, 2, 128, 256, 64, 1, False, 1.0),     # two kv blocks (stage ring, accumulate)
+    (2, 6, 1370, 1370, 64, 1, False, 1.0),   # DINOv2 shape, ragged tails
+    (1, 8, 128, 128, 48, 1, False, 1.0),     # d=48 single tile
+    (2, 8, 1369, 1369, 48, 1, False, 2.0),   # decoder self-attention
+    (1, 8, 300, 6845, 48, 1, False, 3.0),    # cross-attention, long kv, peaky softmax (lazy rescale path)
+    (1, 8, 300, 6845, 48, 4, False, 1.0),    # split-KV + merge
+    (3, 8, 200, 700, 48, 1, True, 1.0),      # shared reference K/V
+])
+def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale):
+    o, ref, lse, lse_ref = run_attn(DT_BF16, B, H, Lq, Lk, d, 64, nsplit, shared, qscale=qscale)
+    assert torch.isfinite(o).all()
+    err = (o - ref).abs()
+    assert err.max() < 0.03, f"max err {err.max().item()}"
+    assert err.mean() < 3e-3
+    assert (lse - lse_ref).abs().max() < 0.02
+
+
+# ------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
+def test_layernorm_residual(dt):
+    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+    rows = 1001
+    h, d = rnd(rows, 384, seed=1, scale=3.0), rnd(rows, 384, seed=2, dtype=adt)
+    g, b = rnd(384, seed=3) * 0.2 + 1, rnd(384, seed=4, scale=0.1)
+    h_out, y, y32 = torch.empty_like(h), torch.empty(rows, 384, device=DEV, dtype=adt), torch.empty_like(h)
+    call("xs_layernorm", P(h), P(d), P(h_out), P(g), P(b), 1e-6, P(y), P(y32), rows, dt, st())
+    x = h.double() + d.double()
+    ref = torch.nn.functional.layer_norm(x, (384,), g.double(), b.double(), 1e-6)
+    assert (h_out.double() - x).abs().max() < 1e-6
+    assert (y32.double() - ref).abs().max() < 1e-5
+    assert (y.double() - ref).abs().max() < (1e-5 if dt == DT_F32 else 0.04)
+    # no residual (do_short_cut=False), in-place y32 over res_in allowed
+    call("xs_layernorm", None, P(d), None, P(g), P(b), 1e-5, P(y), None, rows, dt, st())
+    ref2 = torch.nn.functional.layer_norm(d.double(), (384,), g.double(), b.double(), 1e-5)
+    assert (y.double() - ref2).abs().max() < (1e-5 if dt == DT_F32 else 0.04)
+
+
+@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
+def test_patch_embed_embed_final(dt):
+    from oracle import crossscore_oracle as O
+    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+    I, H, W = 3, 84, 117
+    ph, pw = H // 14, W // 14
+    Pn = ph * pw
+    img = rnd(I, 3, H, W, seed=5)
+    wconv = rnd(384, 3, 14, 14, seed=6, scale=0.05)
+    bias = rnd(384, seed=7, scale=0.1)
+    K = 592 if dt == DT_BF16 else 588
+    w2 = wconv.reshape(384, 588)
+    if dt == DT_BF16:
+        w2 = torch.nn.functional.pad(w2, (0, 4))
+    w2 = w2.to(adt).contiguous()
+    nbytes = _lib.load().xs_workspace_bytes(_lib.OP_PATCH_EMBED, I, H, W, dt)
+    assert nbytes == I * Pn * K * (2 if dt == DT_BF16 else 4)
+    ws = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+    tok = torch.empty(I * Pn, 384, device=DEV, dtype=adt)
+    call("xs_patch_embed", P(img), P(w2), P(bias), P(tok), P(ws), nbytes, I, H, W, dt, st())
+    ref = torch.nn.functional.conv2d(img.double(), wconv.double(), bias.double(), stride=14).flatten(2).transpose(1, 2)
+    tol = 1e-4 if dt == DT_F32 else 0.06
+    assert (tok.double().view(I, Pn, 384) - ref).abs().max() < tol
+
+    # embeddings + first LN
+    cls, pos = rnd(384, seed=8), rnd(Pn + 1, 384, seed=9, scale=0.3)
+    g, b = rnd(384, seed=3) * 0.2 + 1, rnd(384, seed=4, scale=0.1)
+    h = torch.empty(I * (Pn + 1), 384, device=DEV)
+    y = torch.empty(I * (Pn + 1), 384, device=DEV, dtype=adt)
+    call("xs_embed_cls_pos_ln", P(tok), P(cls), P(pos), P(h), P(g), P(b), 1e-6, P(y), I, Pn, dt, st())
+    href = torch.cat([cls.double().expand(I, 1, 384), tok.double().view(I, Pn, 384)], 1) + pos.double()[None]
+    assert (h.double().view(I, Pn + 1, 384) - href).abs().max() < 1e-5
+    yref = torch.nn.functional.layer_norm(href, (384,), g.double(), b.double(), 1e-6)
+    assert (y.double().view(I, Pn + 1, 384) - yref).abs().max() < (1e-4 if dt == DT_F32 else 0.05)
+
+    # final LN + CLS drop + split + PE  (image 0 = query, images 1..2 = references)
+    d = rnd(I * (Pn + 1), 384, seed=11, dtype=adt)
+    pe = rnd(Pn, 384, seed=12)
+    xq32 = torch.empty(Pn, 384, device=DEV)
+    xq = torch.empty(Pn, 384, device=DEV, dtype=adt)
+    mem = torch.empty(2 * Pn, 384, device=DEV, dtype=adt)
+    call("xs_final_ln_drop_cls_add_pe", P(h), P(d), P(g), P(b), 1e-6, P(pe), P(xq32), P(xq), P(mem), I, 1, Pn, dt, st())
+    f = torch.nn.functional.layer_norm(h.double() + d.double(), (384,), g.double(), b.double(), 1e-6)
+    f = f.view(I, Pn + 1, 384)[:, 1:] + pe.double()[None]
+    assert (xq32.double() - f[0]).abs().max() < 1e-4
+    tol = 1e-4 if dt == DT_F32 else 0.05
+    assert (xq.double() - f[0]).abs().max() < tol
+    assert (mem.double().view(2, Pn, 384) - f[1:]).abs().max() < tol
+
+
+def test_table_resamplers():
+    from oracle import crossscore_oracle as O
+    t = rnd(40, 40, 384, seed=1)
+    for oh, ow in [(37, 37), (5, 5), (6, 8), (74, 74), (37, 49)]:
+        out = torch.empty(oh, ow, 384, device=DEV)
+        call("xs_pe_resample_bilinear_ac", P(t), P(out), 40, 40, oh, ow, 384, st())
+        ref = O.bilinear_resize_ac_true(t.cpu().double(), oh, ow)
+        assert (out.cpu().double() - ref).abs().max() < 2e-5
+    t = rnd(37, 37, 384, seed=2, scale=0.3)
+    for oh, ow in [(5, 5), (6, 8), (74, 74), (37, 49), (12, 11)]:
+        out = torch.empty(oh, ow, 384, device=DEV)
+        call("xs_pos_embed_resample_bicubic", P(t), P(out), 37, 37, oh, ow, 384, st())
+        ref = O.bicubic_resize_ac_false(t.cpu().double(), oh, ow)
+        assert (out.cpu().double() - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
+@pytest.mark.parametrize("use_tanh,power", [(0, 1.0), (1, 1.0), (0, 2.0), (0, 0.5)])
+def test_head_score_jigsaw(dt, use_tanh, power):
+    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+    B, ph, pw = 2, 9, 17  # 153 tokens per map: straddles the 128-row tile, crosses the batch boundary
+    R = B * ph * pw
+    A = rnd(R, 384, seed=1, dtype=adt)
+    W = rnd(196, 384, seed=2, scale=0.1)
+    bias = rnd(196, seed=3, scale=0.05)
+    Wk, bk = W, bias
+    if dt == DT_BF16:
+        Wk = torch.nn.functional.pad(W, (0, 0, 0, 28))
+        bk = torch.nn.functional.pad(bias, (0, 28)).contiguous()
+    Wk = Wk.to(adt).contiguous()
+    score = torch.full((B, 14 * ph, 14 * pw), float("nan"), device=DEV)
+    call("xs_head_score_jigsaw", P(A), 384, P(Wk), 384, P(bk), P(score), B, ph, pw, 384, use_tanh, power, dt, st())
+    z = A.double() @ Wk.double()[:196].T + bias.double()
+    s = torch.tanh(z) if use_tanh else torch.sigmoid(z)
+    if power != 1.0:
+        s = s ** power
+    ref = s.view(B, ph, pw, 14, 14).permute(0, 1, 3, 2, 4).reshape(B, 14 * ph, 14 * pw)
+    tol = 1e-5 if dt == DT_F32 else 0.02
+    assert torch.isfinite(score).all()
+    assert (score.double() - ref).abs().max() < tol
+
+
+@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
+def test_attn_probs_one_head(dt):
+    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+    B, H, Lq, Lk, d = 2, 8, 50, 120, 48
+    slot = 48 if dt == DT_F32 else 64
+    q, k = rnd(B, Lq, H * slot, seed=1, dtype=adt), rnd(B, Lk, H * slot, seed=2, dtype=adt)
+    scale = 1 / math.sqrt(d)
+    head = 5
+    qd = q.double().view(B, Lq, H, slot)[:, :, head, :d]
+    kd = k.double().view(B, Lk, H, slot)[:, :, head, :d]
+    s = qd @ kd.transpose(-1, -2) * scale
+    lse = torch.zeros(B, H, Lq, device=DEV)
+    lse[:, head] = torch.logsumexp(s, -1).float()
+    probs = torch.empty(B, Lq, Lk, device=DEV)
+    call("xs_attn_probs_one_head", P(q), P(k), P(lse), P(probs), B, H, head, Lq, Lk, d, slot, H * slot, Lq * H * slot,
+         H * slot, Lk * H * slot, scale, dt, st())
+    assert (probs.double() - torch.softmax(s, -1)).abs().max() < 1e-5

