@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the CrossScore inference hot path (BASELINE.json metric: score maps/s, 518x518, 5 refs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision bf16|fp32]
+
+One "step" = one forward of B=32 queries x 5 reference views at 518x518 (BASELINE.json configs[1]) per GPU.
+N>1 is launched by torchrun (one rank per GPU): queries shard across ranks with no data-path collective
+(weak scaling); NCCL is used only for the barrier and the max-over-ranks time.
+Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle port of the reference path on the
+host cores (the reference is pure Python/PyTorch and is not present on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 518
+N_REF = 5
+C = 384
+
+
+def flops_per_map(P=1369, N=N_REF):
+    """Algorithmic FLOPs per score map (SURVEY.md section 8d convention)."""
+    T, M = P + 1, N * P
+    f_dino = 2 * P * 588 * C + 12 * (2 * T * C * 3 * C + 4 * T * T * C + 2 * T * C * C + 4 * T * C * 4 * C)
+    f_dec = 2 * (2 * P * C * 3 * C + 4 * P * P * C + 2 * P * C * C + 2 * P * C * C + 2 * M * C * 2 * C
+                 + 4 * P * M * C + 2 * P * C * C + 4 * P * C * C)
+    f_head = 2 * P * C * C + 2 * P * C * 196
+    return (1 + N) * f_dino + f_dec + f_head
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tensor_burst": p["bf16_tflops"], "tensor_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tensor_burst": 1590.0, "tensor_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(steps, warmup, min_seconds=0.0):
+    """maps/s of the CPU oracle port on cfg 1 (1 query + 5 refs, 518x518), all host threads, fp32."""
+    import torch
+    from crossscore_b200.synthetic import make_inputs, make_state_dict
+    from oracle import crossscore_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    O.FAST = True  # torch's fused CPU kernels (SDPA / layer_norm / gelu): what the reference itself calls on CPU
+    sd = make_state_dict(1)
+    q, r = make_inputs(1, N_REF, H, W, seed=0)
+    with torch.inference_mode():
+        for _ in range(warmup):
+            O.crossscore_forward(sd, q, r, dt=torch.float32)
+        times = []
+        t_all = time.perf_counter()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.crossscore_forward(sd, q, r, dt=torch.float32)
+            times.append(time.perf_counter() - t0)
+        while time.perf_counter() - t_all < min_seconds:
+            t0 = time.perf_counter()
+            O.crossscore_forward(sd, q, r, dt=torch.float32)
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return len(times) / total, total / len(times), torch.get_num_threads(), len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    rate, sec, cores, n = cpu_oracle_rate(steps, min(args.warmup, 1))
+    sample = f"{n} forwards of cfg-1 (1 query + {N_REF} refs, {H}x{W}, fp32 CPU oracle port on torch fused CPU ops), {sec:.2f} s each"
+    line = {
+        "impl": "reference", "metric": "score maps/s (518x518, 5 refs)", "value": rate, "unit": "maps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg1: 1 query x 5 refs, 518x518 per step (bounded sample of cfg2 batch-32)",
+                   "global_batch": 1, "image": [H, W], "n_ref": N_REF},
+        "cpu_baseline": {"value": rate, "unit": "maps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from crossscore_b200 import CrossScoreNet, _lib, default_cfg
+    from crossscore_b200.runner import HostScorer
+    from crossscore_b200.synthetic import make_inputs, make_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, args.warmup
+
+    net = CrossScoreNet(default_cfg(), precision=args.precision)
+    net.load_state_dict(make_state_dict(1))
+    net = net.to(dev).eval()
+    q, r = make_inputs(B, N_REF, H, W, seed=100 + rank)
+    q_dev, r_dev = q.to(dev), r.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for _ in range(Wm):
+        out = net(q_dev, r_dev, False, 0, False)["score_map_ref_cross"]
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = net(q_dev, r_dev, False, 0, False)["score_map_ref_cross"]
+    e1.record()
+    barrier()
+    launches = _lib.launches() - l0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    assert torch.isfinite(out).all()
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- end to end: pinned host inputs -> public API -> host score maps ---------------------------------
+    qh, rh = q.pin_memory(), r.pin_memory()
+    scorer = HostScorer(net, dev)
+    for _ in range(2):
+        scorer.submit(qh, rh)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        host_out = scorer.submit(qh, rh)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    assert bool(torch.isfinite(host_out).all())
+
+    # ---- per-kernel roofline (instrumented pass, CUDA events on the launching stream) --------------------
+    eng = net._engine(dev)
+    eng.prof = []
+    net(q_dev, r_dev, False, 0, False)
+    torch.cuda.synchronize()
+    agg = {}
+    for tag, fl, nb, s, e in eng.prof:
+        a = agg.setdefault(tag, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += fl
+        a[2] += nb
+        a[3] += s.elapsed_time(e)
+    eng.prof = None
+    pk = peaks()
+    step_ms = sum(a[3] for a in agg.values())
+    kernels = {}
+    for tag, (n, fl, nb, ms) in sorted(agg.items(), key=lambda kv: -kv[1][3]):
+        ent = {"launches": n, "ms": round(ms, 4), "share": round(ms / step_ms, 4)}
+        if fl > 0:
+            ent["tflops"] = round(fl / (ms * 1e-3) / 1e12, 2)
+            ent["frac_of_tensor_peak_sustained"] = round(ent["tflops"] / pk["tensor_sustained"], 4)
+        elif nb > 0:
+            ent["gbs"] = round(nb / (ms * 1e-3) / 1e9, 1)
+            ent["frac_of_hbm_peak"] = round(ent["gbs"] / pk["hbm"], 4)
+        kernels[tag] = ent
+    top = next(iter(kernels))
+    tent = agg[top]
+    if tent[1] > 0:
+        ach = tent[1] / tent[0] / (tent[3] / tent[0] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor_sustained"], "traffic": None,
+                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "algorithmic_flops_per_launch": tent[1] / tent[0], "avg_launch_ms": tent[3] / tent[0]}
+    else:
+        ach = tent[2] / tent[0] / (tent[3] / tent[0] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"]}
+    attn_fl = sum(a[1] for t, a in agg.items() if t.startswith("attn_") and a[1] > 0)
+    attn_ms = sum(a[3] for t, a in agg.items() if t.startswith("attn_") and a[1] > 0)
+    attn_tf = attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores, n = cpu_oracle_rate(2, 1)
+        cpu = {"value": rate, "unit": "maps/s", "cores": cores, "kind": "port",
+               "sample": f"{n} forwards of cfg-1 (1 query + {N_REF} refs, {H}x{W}), fp32 CPU oracle port on torch fused CPU ops, "
+                         f"{sec:.2f} s each, after 1 warm-up"}
+
+    fpm = flops_per_map()
+    line = {
+        "metric": "score maps/s (518x518, 5 refs)", "value": value, "unit": "maps/s", "n_gpus": world,
+        "steps": K, "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2: batch {B} queries x {N_REF} refs, {H}x{W}, per GPU (queries shard across ranks)",
+                   "global_batch": world * B, "image": [H, W], "n_ref": N_REF, "precision": args.precision,
+                   "l2": "inputs exceed L2 (%.0f MB of images per step per GPU)" % ((q.numel() + r.numel()) * 4 / 1e6),
+                   "weights": "seeded synthetic state_dict (real ckpt is a git-lfs pointer offline)"},
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "maps/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": scorer.h2d_bytes(qh, rh), "d2h_bytes_per_step": int(host_out.numel() * 4)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "model_tflops": value * fpm / 1e12,
+        "model_frac_of_tensor_peak_sustained": value * fpm / 1e12 / world / pk["tensor_sustained"],
+        "attention_tflops": attn_tf, "attention_frac_of_bf16_peak_sustained": attn_tf / pk["tensor_sustained"],
+        "attention_frac_of_bf16_peak_burst": attn_tf / pk["tensor_burst"],
+        "kernels": kernels,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun when called directly with --gpus N
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)]
+            cmd += [a for a in sys.argv[1:]]
+            sys.exit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

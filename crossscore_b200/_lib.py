@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcrossscore_sm100a.so")
 
-DT_BF16, DT_F32 = 0, 1
+DT_BF16, DT_F32, DT_TF32 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY = 0, 1, 2, 3
 OP_PATCH_EMBED = 1
 
@@ -24,12 +24,12 @@ SIGNATURES = {
     "xs_device_check": (_i, []),
     "xs_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "xs_patch_embed": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _p]),
-    "xs_embed_cls_pos_ln": (_i, [_p, _p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _p]),
+    "xs_embed_cls_pos_ln": (_i, [_p, _i, _p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _p]),
     "xs_layernorm": (_i, [_p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p]),
     "xs_final_ln_drop_cls_add_pe": (_i, [_p, _p, _p, _p, _f, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "xs_pe_resample_bilinear_ac": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "xs_pos_embed_resample_bicubic": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
-    "xs_gemm_bias_act": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "xs_gemm_bias_act": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_lse_merge": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "xs_head_score_jigsaw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),

@@ -78,9 +78,9 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
 }
 
 // kernels (defined in the other translation units)
-int gemm_bf16_tc(const void*, int, const void*, int, const float*, void*, int, int, int, int, int, cudaStream_t);
-int head_jigsaw_bf16_tc(const void*, int, const void*, int, const float*, float*, int, int, int, int, int, float,
-                        cudaStream_t);
+int gemm_tc(const void*, int, const void*, int, const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int head_jigsaw_tc(const void*, int, const void*, int, const float*, float*, int, int, int, int, int, float, int,
+                   cudaStream_t);
 int flash_attn_bf16_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long,
                        long long, long long, long long, int, int, int, float, cudaStream_t);
 int gemm_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, cudaStream_t);
@@ -90,8 +90,8 @@ int flash_attn_f32(const float*, const float*, const float*, float*, float*, int
                    long long, long long, long long, int, int, float, cudaStream_t);
 int rows_add_ln(const float*, const void*, float*, const float*, const float*, float, void*, float*, int, int,
                 cudaStream_t);
-int rows_embed_ln(const void*, const float*, const float*, float*, const float*, const float*, float, void*, int, int,
-                  int, cudaStream_t);
+int rows_embed_ln(const void*, int, const float*, const float*, float*, const float*, const float*, float, void*, int,
+                  int, int, cudaStream_t);
 int rows_final_ln_pe(const float*, const void*, const float*, const float*, float, const float*, float*, void*, void*,
                      int, int, int, int, cudaStream_t);
 int rows_im2col14(const float*, void*, int, int, int, int, int, cudaStream_t);
@@ -102,6 +102,7 @@ int rows_attn_probs(const void*, const void*, const float*, float*, int, int, in
                     long long, long long, long long, float, int, cudaStream_t);
 
 static inline int kpad_for(int dtype) { return dtype == XS_BF16 ? 592 : 588; }
+static inline int elem_bytes(int dtype) { return dtype == XS_BF16 ? 2 : 4; }
 
 }  // namespace xs
 
@@ -125,7 +126,7 @@ int xs_device_check(void) {
 size_t xs_workspace_bytes(int op, int a, int b, int c, int dtype) {
   if (op == XS_OP_PATCH_EMBED) {
     const size_t P = (size_t)(b / 14) * (size_t)(c / 14);
-    return (size_t)a * P * (size_t)kpad_for(dtype) * (dtype == XS_BF16 ? 2 : 4);
+    return (size_t)a * P * (size_t)kpad_for(dtype) * (size_t)elem_bytes(dtype);
   }
   return 0;
 }
@@ -137,18 +138,22 @@ int xs_patch_embed(const float* img, const void* w, const float* bias, void* tok
   XS_CHECK_ARG(n_images > 0 && ph > 0 && pw > 0, "patch_embed: bad dims I=%d H=%d W=%d", n_images, H, W);
   XS_CHECK_ARG(workspace_bytes >= xs_workspace_bytes(XS_OP_PATCH_EMBED, n_images, H, W, dtype),
                "patch_embed: workspace too small (%zu bytes)", workspace_bytes);
+  XS_CHECK_ARG(dtype == XS_BF16 || dtype == XS_F32 || dtype == XS_TF32, "patch_embed: unknown dtype %d", dtype);
   const int Kpad = kpad_for(dtype);
-  int rc = rows_im2col14(img, workspace, n_images, H, W, Kpad, dtype, st);
+  int rc = rows_im2col14(img, workspace, n_images, H, W, Kpad, dtype == XS_BF16 ? XS_BF16 : XS_F32, st);
   if (rc) return rc;
   const int M = n_images * ph * pw;
-  if (dtype == XS_BF16) return gemm_bf16_tc(workspace, Kpad, w, Kpad, bias, tok, 384, M, 384, Kpad, ACT_NONE, st);
+  if (dtype == XS_BF16) return gemm_tc(workspace, Kpad, w, Kpad, bias, tok, 384, M, 384, Kpad, ACT_NONE, 0, 0, st);
+  if (dtype == XS_TF32) return gemm_tc(workspace, Kpad, w, Kpad, bias, tok, 384, M, 384, Kpad, ACT_NONE, 1, 1, st);
   return gemm_f32(static_cast<const float*>(workspace), Kpad, static_cast<const float*>(w), Kpad, bias,
                   static_cast<float*>(tok), 384, M, 384, Kpad, ACT_NONE, st);
 }
 
-int xs_embed_cls_pos_ln(const void* tok, const float* cls, const float* pos, float* h, const float* gamma,
-                        const float* beta, float eps, void* y, int n_images, int P, int dtype, xs_stream_t stream) {
-  return rows_embed_ln(tok, cls, pos, h, gamma, beta, eps, y, n_images, P, dtype, static_cast<cudaStream_t>(stream));
+int xs_embed_cls_pos_ln(const void* tok, int tok_dtype, const float* cls, const float* pos, float* h,
+                        const float* gamma, const float* beta, float eps, void* y, int n_images, int P, int dtype,
+                        xs_stream_t stream) {
+  return rows_embed_ln(tok, tok_dtype, cls, pos, h, gamma, beta, eps, y, n_images, P, dtype,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int xs_layernorm(const float* res_in, const void* delta, float* res_out, const float* gamma, const float* beta,
@@ -174,12 +179,16 @@ int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw
 }
 
 int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
-                     int N, int K, int act, int dtype, xs_stream_t stream) {
+                     int N, int K, int act, int dtype, int out_dtype, xs_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == XS_BF16) return gemm_bf16_tc(A, lda, W, ldw, bias, out, ldc, M, N, K, act, st);
-  if (dtype == XS_F32)
+  XS_CHECK_ARG(out_dtype == XS_BF16 || out_dtype == XS_F32, "gemm: out_dtype must be bf16 or fp32");
+  if (dtype == XS_BF16 || dtype == XS_TF32)
+    return gemm_tc(A, lda, W, ldw, bias, out, ldc, M, N, K, act, dtype == XS_TF32, out_dtype == XS_F32, st);
+  if (dtype == XS_F32) {
+    XS_CHECK_ARG(out_dtype == XS_F32, "gemm(fp32): output must be fp32");
     return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias,
                     static_cast<float*>(out), ldc, M, N, K, act, st);
+  }
   set_last_error("gemm: unknown dtype %d", dtype);
   return -1;
 }
@@ -213,7 +222,8 @@ int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float*
 int xs_head_score_jigsaw(const void* A, int lda, const void* W, int ldw, const float* bias, float* score, int B,
                          int ph, int pw, int K, int use_tanh, float power, int dtype, xs_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == XS_BF16) return head_jigsaw_bf16_tc(A, lda, W, ldw, bias, score, B, ph, pw, K, use_tanh, power, st);
+  if (dtype == XS_BF16 || dtype == XS_TF32)
+    return head_jigsaw_tc(A, lda, W, ldw, bias, score, B, ph, pw, K, use_tanh, power, dtype == XS_TF32, st);
   if (dtype == XS_F32)
     return head_jigsaw_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias, score, B, ph,
                            pw, K, use_tanh, power, st);

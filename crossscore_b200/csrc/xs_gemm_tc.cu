@@ -1,4 +1,7 @@
-// bf16 linear layers on tcgen05 tensor cores:  out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N])
+// Linear layers on tcgen05 tensor cores:  out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N])
+// Operands are bf16 (kind::f16, K=16 per instruction) or fp32 read as TF32 (kind::tf32, K=8; used for the
+// small precision-critical GEMMs: patch embedding, decoder projections/FFN and the head, ~2 % of the FLOPs);
+// the output tile is stored as bf16 or fp32.
 //
 // One persistent, warp-specialised kernel (one CTA per SM):
 //   warp 0      TMA producer   A tile [128 x 64] and W tile [BN x 64] (128B-swizzled) into a smem ring
@@ -24,7 +27,9 @@ constexpr int GEMM_THREADS = 256;
 constexpr int ACC_STAGE_COLS = 256;  // TMEM column offset between the two accumulator stages
 constexpr int JIG_LD = 197;          // padded row length of the fp32 score staging tile
 
-enum Epi : int { EPI_BF16 = 0, EPI_JIGSAW = 1 };
+enum Epi : int { EPI_STORE = 0, EPI_JIGSAW = 1 };
+enum InT : int { IN_BF16 = 0, IN_TF32 = 1 };
+enum OutT : int { OUT_BF16 = 0, OUT_F32 = 1 };
 
 struct JigsawParams {
   float* score;  // (B, 14*ph, 14*pw) fp32
@@ -40,7 +45,7 @@ template <int BN, int STAGES, int EPI>
 struct GemmSmem {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
-  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_BF16) ? 2 * GEMM_BM * 128 : GEMM_BM * JIG_LD * 4;
+  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 2 * GEMM_BM * 128 : GEMM_BM * JIG_LD * 4;
   static constexpr uint32_t OFF_A = 0;
   static constexpr uint32_t OFF_B = OFF_A + STAGES * A_BYTES;
   static constexpr uint32_t OFF_STAGING = OFF_B + STAGES * B_BYTES;
@@ -49,7 +54,7 @@ struct GemmSmem {
   static constexpr uint32_t TOTAL = OFF_BAR + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment of the base
 };
 
-template <int BN, int STAGES, int EPI, int ACT>
+template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
@@ -72,13 +77,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
   const int num_n = N / BN;
-  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+  constexpr int BKE = (IN == IN_TF32) ? 32 : 64;  // elements per 128-byte smem row
+  const int num_k = (K + BKE - 1) / BKE;
   const int num_tiles = num_m * num_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
-    if constexpr (EPI == EPI_BF16) tma_prefetch_desc(&tmC);
+    if constexpr (EPI == EPI_STORE) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -103,14 +109,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
-        tma_load_2d(smA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-        tma_load_2d(smB + stage * L::B_BYTES, &tmW, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+        tma_load_2d(smA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BKE, m_blk * GEMM_BM);
+        tma_load_2d(smB + stage * L::B_BYTES, &tmW, &full_bar[stage], kb * BKE, n_blk * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+    constexpr uint32_t idesc = (IN == IN_TF32) ? umma_idesc_tf32(GEMM_BM, BN) : umma_idesc_bf16(GEMM_BM, BN, 0, 0);
     uint32_t stage = 0, phase = 0, acc_stage = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
@@ -122,10 +128,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_addr = smem_u32(smA + stage * L::A_BYTES);
         const uint32_t b_addr = smem_u32(smB + stage * L::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
+        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row (16 bf16 or 8 tf32 each)
           const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
           const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (IN == IN_TF32) umma_ss_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -146,8 +153,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc_stage * ACC_STAGE_COLS + (static_cast<uint32_t>(q * 32) << 16);
 
-      if constexpr (EPI == EPI_BF16) {
-        constexpr int NCHUNK = BN / 64;
+      if constexpr (EPI == EPI_STORE) {
+        constexpr int CW = (OUT == OUT_F32) ? 32 : 64;  // columns per 128-byte staging row
+        constexpr int NCHUNK = BN / CW;
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
           const uint32_t buf = chunk_counter & 1;
@@ -156,37 +164,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (epi_tid == 0) tma_store_wait_read<1>();
           named_bar_sync(1, 128);
           uint32_t v0[32], v1[32];
-          tmem_ld32(taddr0 + c * 64, v0);
-          tmem_ld32(taddr0 + c * 64 + 32, v1);
+          tmem_ld32(taddr0 + c * CW, v0);
+          if constexpr (OUT == OUT_BF16) tmem_ld32(taddr0 + c * CW + 32, v1);
           tc_wait_ld();
           if (c == NCHUNK - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
           }
-          const int n0 = n_blk * BN + c * 64;
+          const int n0 = n_blk * BN + c * CW;
           uint8_t* srow = staging + buf * (GEMM_BM * 128) + epi_tid * 128;
           const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+          // 128B swizzle: 16-byte chunk index XOR (row mod 8); conflict-free for thread==row writes
+          if constexpr (OUT == OUT_BF16) {
 #pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) {
-            const float4 ba = __ldg(b4 + j8 * 2), bb = __ldg(b4 + j8 * 2 + 1);
-            const uint32_t* v = (j8 < 4) ? v0 : v1;
-            const int o = (j8 & 3) * 8;
-            const float x0 = apply_act<ACT>(__uint_as_float(v[o + 0]) + ba.x);
-            const float x1 = apply_act<ACT>(__uint_as_float(v[o + 1]) + ba.y);
-            const float x2 = apply_act<ACT>(__uint_as_float(v[o + 2]) + ba.z);
-            const float x3 = apply_act<ACT>(__uint_as_float(v[o + 3]) + ba.w);
-            const float x4 = apply_act<ACT>(__uint_as_float(v[o + 4]) + bb.x);
-            const float x5 = apply_act<ACT>(__uint_as_float(v[o + 5]) + bb.y);
-            const float x6 = apply_act<ACT>(__uint_as_float(v[o + 6]) + bb.z);
-            const float x7 = apply_act<ACT>(__uint_as_float(v[o + 7]) + bb.w);
-            uint4 pk;
-            pk.x = pack_bf16x2(x0, x1);
-            pk.y = pack_bf16x2(x2, x3);
-            pk.z = pack_bf16x2(x4, x5);
-            pk.w = pack_bf16x2(x6, x7);
-            // 128B swizzle: 16-byte chunk index XOR (row mod 8); conflict-free for thread==row writes
-            *reinterpret_cast<uint4*>(srow + ((j8 ^ (epi_tid & 7)) << 4)) = pk;
+            for (int j8 = 0; j8 < 8; ++j8) {
+              const float4 ba = __ldg(b4 + j8 * 2), bb = __ldg(b4 + j8 * 2 + 1);
+              const uint32_t* v = (j8 < 4) ? v0 : v1;
+              const int o = (j8 & 3) * 8;
+              const float x0 = apply_act<ACT>(__uint_as_float(v[o + 0]) + ba.x);
+              const float x1 = apply_act<ACT>(__uint_as_float(v[o + 1]) + ba.y);
+              const float x2 = apply_act<ACT>(__uint_as_float(v[o + 2]) + ba.z);
+              const float x3 = apply_act<ACT>(__uint_as_float(v[o + 3]) + ba.w);
+              const float x4 = apply_act<ACT>(__uint_as_float(v[o + 4]) + bb.x);
+              const float x5 = apply_act<ACT>(__uint_as_float(v[o + 5]) + bb.y);
+              const float x6 = apply_act<ACT>(__uint_as_float(v[o + 6]) + bb.z);
+              const float x7 = apply_act<ACT>(__uint_as_float(v[o + 7]) + bb.w);
+              uint4 pk;
+              pk.x = pack_bf16x2(x0, x1);
+              pk.y = pack_bf16x2(x2, x3);
+              pk.z = pack_bf16x2(x4, x5);
+              pk.w = pack_bf16x2(x6, x7);
+              *reinterpret_cast<uint4*>(srow + ((j8 ^ (epi_tid & 7)) << 4)) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 ba = __ldg(b4 + j4);
+              float4 o4;
+              o4.x = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 0]) + ba.x);
+              o4.y = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 1]) + ba.y);
+              o4.z = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 2]) + ba.z);
+              o4.w = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 3]) + ba.w);
+              *reinterpret_cast<float4*>(srow + ((j4 ^ (epi_tid & 7)) << 4)) = o4;
+            }
           }
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
@@ -244,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc_stage ^= 1;
       if (acc_stage == 0) acc_phase ^= 1;
     }
-    if constexpr (EPI == EPI_BF16) {
+    if constexpr (EPI == EPI_STORE) {
       if (epi_tid == 0) tma_store_wait_all<0>();
     }
   }
@@ -260,40 +281,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int EPI, int ACT>
+template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                        int N, int K, JigsawParams jp, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI>;
+  constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
+  constexpr int OUT_B = (OUT == OUT_F32) ? 4 : 2;
+  constexpr uint32_t BKE = 128 / IN_B;
   CUtensorMap tmA, tmW, tmC;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    uint64_t strides[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {GEMM_BK, GEMM_BM};
-    int rc = make_tmap(&tmA, A, 2, 2, dims, strides, box, SWZ_128B);
+    uint64_t strides[1] = {(uint64_t)lda * IN_B};
+    uint32_t box[2] = {BKE, GEMM_BM};
+    int rc = make_tmap(&tmA, A, IN_B, 2, dims, strides, box, SWZ_128B);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
-    uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
-    int rc = make_tmap(&tmW, W, 2, 2, dims, strides, box, SWZ_128B);
+    uint64_t strides[1] = {(uint64_t)ldw * IN_B};
+    uint32_t box[2] = {BKE, (uint32_t)BN};
+    int rc = make_tmap(&tmW, W, IN_B, 2, dims, strides, box, SWZ_128B);
     if (rc) return rc;
   }
-  if (EPI == EPI_BF16) {
+  if (EPI == EPI_STORE) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
-    uint64_t strides[1] = {(uint64_t)ldc * 2};
-    uint32_t box[2] = {64, GEMM_BM};
-    int rc = make_tmap(&tmC, out, 2, 2, dims, strides, box, SWZ_128B);
+    uint64_t strides[1] = {(uint64_t)ldc * OUT_B};
+    uint32_t box[2] = {128 / OUT_B, GEMM_BM};
+    int rc = make_tmap(&tmC, out, OUT_B, 2, dims, strides, box, SWZ_128B);
     if (rc) return rc;
   } else {
     tmC = tmA;  // unused
   }
-  auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
-    attr_done = true;
-  }
+  auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT, IN, OUT>;
+  XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
   const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmW, tmC, bias, M, N, K, jp);
@@ -301,41 +321,63 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
   return 0;
 }
 
-template <int BN, int STAGES>
+#define XS_GEMM_ARGS A, lda, W, ldw, bias, out, ldc, M, N, K, jp, stream
+
+template <int BN, int STAGES, int IN, int OUT>
 static int dispatch_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                         int N, int K, int act, cudaStream_t stream) {
   JigsawParams jp{};
   switch (act) {
-    case ACT_NONE: return launch_gemm<BN, STAGES, EPI_BF16, ACT_NONE>(A, lda, W, ldw, bias, out, ldc, M, N, K, jp, stream);
-    case ACT_GELU: return launch_gemm<BN, STAGES, EPI_BF16, ACT_GELU>(A, lda, W, ldw, bias, out, ldc, M, N, K, jp, stream);
-    case ACT_RELU: return launch_gemm<BN, STAGES, EPI_BF16, ACT_RELU>(A, lda, W, ldw, bias, out, ldc, M, N, K, jp, stream);
-    case ACT_LEAKY: return launch_gemm<BN, STAGES, EPI_BF16, ACT_LEAKY>(A, lda, W, ldw, bias, out, ldc, M, N, K, jp, stream);
+    case ACT_NONE: return launch_gemm<BN, STAGES, EPI_STORE, ACT_NONE, IN, OUT>(XS_GEMM_ARGS);
+    case ACT_GELU: return launch_gemm<BN, STAGES, EPI_STORE, ACT_GELU, IN, OUT>(XS_GEMM_ARGS);
+    case ACT_RELU: return launch_gemm<BN, STAGES, EPI_STORE, ACT_RELU, IN, OUT>(XS_GEMM_ARGS);
+    case ACT_LEAKY: return launch_gemm<BN, STAGES, EPI_STORE, ACT_LEAKY, IN, OUT>(XS_GEMM_ARGS);
   }
   set_last_error("xs_gemm_bias_act: unknown activation %d", act);
   return -1;
 }
 
-// bf16 GEMM entry used by xs_api.cu.  N must be a multiple of 192 or 256; K, lda, ldw, ldc multiples of 8.
-int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N,
-                 int K, int act, cudaStream_t stream) {
+// Tensor-core GEMM entry used by xs_api.cu.  in_tf32: A/W are fp32 (TF32 multiply), else bf16.
+// N must be a multiple of 192 or 256; row pitches must be multiples of 16 bytes.
+int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
+            int act, int in_tf32, int out_f32, cudaStream_t stream) {
+  const int al = in_tf32 ? 4 : 8;
+  const int cl = out_f32 ? 4 : 8;
   XS_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  XS_CHECK_ARG((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && (ldc % 8) == 0,
-               "gemm: K/lda/ldw/ldc must be multiples of 8 elements (16 bytes) for TMA, got K=%d lda=%d ldw=%d ldc=%d",
-               K, lda, ldw, ldc);
+  XS_CHECK_ARG((K % al) == 0 && (lda % al) == 0 && (ldw % al) == 0 && (ldc % cl) == 0,
+               "gemm: K/lda/ldw/ldc must be multiples of 16 bytes for TMA, got K=%d lda=%d ldw=%d ldc=%d", K, lda, ldw,
+               ldc);
   XS_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                "gemm: pointers must be 16-byte aligned");
-  if (N % 192 == 0 && (N % 256 != 0 || N < 1024)) return dispatch_act<192, 4>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
-  if (N % 256 == 0) return dispatch_act<256, 3>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
-  set_last_error("gemm: N=%d must be a multiple of 192 or 256 (pad the weight rows)", N);
-  return -1;
+  const bool use192 = (N % 192 == 0) && (N % 256 != 0 || N < 1024);
+  XS_CHECK_ARG(use192 || N % 256 == 0, "gemm: N=%d must be a multiple of 192 or 256 (pad the weight rows)", N);
+  if (!in_tf32 && !out_f32) {
+    if (use192) return dispatch_act<192, 4, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+    return dispatch_act<256, 3, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+  }
+  JigsawParams jp{};
+  if (!in_tf32 && out_f32) {  // bf16 operands, fp32 result (residual deltas kept unrounded)
+    XS_CHECK_ARG(act == ACT_NONE, "gemm: bf16->fp32 supports act=NONE only");
+    if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32>(XS_GEMM_ARGS);
+    return launch_gemm<256, 3, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32>(XS_GEMM_ARGS);
+  }
+  if (in_tf32 && out_f32) {
+    if (use192) return dispatch_act<192, 4, IN_TF32, OUT_F32>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+    return dispatch_act<256, 3, IN_TF32, OUT_F32>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+  }
+  // tf32 operands, bf16 result (decoder Q/K/V projections feeding the bf16 attention kernel)
+  XS_CHECK_ARG(act == ACT_NONE, "gemm: tf32->bf16 supports act=NONE only");
+  if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_TF32, OUT_BF16>(XS_GEMM_ARGS);
+  return launch_gemm<256, 3, EPI_STORE, ACT_NONE, IN_TF32, OUT_BF16>(XS_GEMM_ARGS);
 }
 
 // head.2 Linear (384 -> 196, weight rows padded to 224) + sigmoid/tanh (+pow) + jigsaw scatter
-int head_jigsaw_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias, float* score, int B, int ph,
-                        int pw, int K, int use_tanh, float power, cudaStream_t stream) {
+int head_jigsaw_tc(const void* A, int lda, const void* W, int ldw, const float* bias, float* score, int B, int ph,
+                   int pw, int K, int use_tanh, float power, int in_tf32, cudaStream_t stream) {
+  const int al = in_tf32 ? 4 : 8;
   XS_CHECK_ARG(B > 0 && ph > 0 && pw > 0, "head_jigsaw: empty problem");
-  XS_CHECK_ARG((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0, "head_jigsaw: K/lda/ldw must be multiples of 8");
+  XS_CHECK_ARG((K % al) == 0 && (lda % al) == 0 && (ldw % al) == 0, "head_jigsaw: K/lda/ldw must be 16-byte multiples");
   JigsawParams jp;
   jp.score = score;
   jp.P = ph * pw;
@@ -344,7 +386,10 @@ int head_jigsaw_bf16_tc(const void* A, int lda, const void* W, int ldw, const fl
   jp.HWout = 14 * ph * 14 * pw;
   jp.use_tanh = use_tanh;
   jp.power = power;
-  return launch_gemm<224, 2, EPI_JIGSAW, ACT_NONE>(A, lda, W, ldw, bias, nullptr, 0, B * ph * pw, 224, K, jp, stream);
+  void* out = nullptr;
+  const int ldc = 0, M = B * ph * pw, N = 224;
+  if (in_tf32) return launch_gemm<224, 2, EPI_JIGSAW, ACT_NONE, IN_TF32, OUT_F32>(XS_GEMM_ARGS);
+  return launch_gemm<224, 2, EPI_JIGSAW, ACT_NONE, IN_BF16, OUT_F32>(XS_GEMM_ARGS);
 }
 
 }  // namespace xs

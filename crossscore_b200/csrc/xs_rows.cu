@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(256) add_ln_kernel(const float* __restrict__ r
 // ---------------------------------------------------------------------------------------------
 // DINOv2 embeddings: h[i,0] = cls + pos[0]; h[i,1+p] = tok[i,p] + pos[1+p];  y = LN(h; layer-0 norm1)
 // ---------------------------------------------------------------------------------------------
-template <typename AT>
-__global__ void __launch_bounds__(256) embed_ln_kernel(const AT* __restrict__ tok, const float* __restrict__ cls,
+template <typename AT, typename TT>
+__global__ void __launch_bounds__(256) embed_ln_kernel(const TT* __restrict__ tok, const float* __restrict__ cls,
                                                        const float* __restrict__ pos, float* __restrict__ h,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const AT* __restrict__ to
     const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * C + c));
     float4 a;
     if (t == 0) a = __ldg(reinterpret_cast<const float4*>(cls + c));
-    else a = Pack4<AT>::load(tok + (static_cast<size_t>(img) * P + (t - 1)) * C + c);
+    else a = Pack4<TT>::load(tok + (static_cast<size_t>(img) * P + (t - 1)) * C + c);
     x.v[i] = make_float4(a.x + pe.x, a.y + pe.y, a.z + pe.z, a.w + pe.w);
   }
   const size_t base = static_cast<size_t>(row) * C;
@@ -372,13 +372,22 @@ int rows_add_ln(const float* res_in, const void* delta, float* res_out, const fl
   return 0;
 }
 
-int rows_embed_ln(const void* tok, const float* cls, const float* pos, float* h, const float* gamma,
+int rows_embed_ln(const void* tok, int tok_dtype, const float* cls, const float* pos, float* h, const float* gamma,
                   const float* beta, float eps, void* y, int I, int P, int dtype, cudaStream_t stream) {
   XS_CHECK_ARG(I > 0 && P > 0, "embed_ln: I=%d P=%d", I, P);
   const long long rows = static_cast<long long>(I) * (P + 1);
   const int grid = static_cast<int>((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
-  XS_DISPATCH_AT(dtype, (embed_ln_kernel<AT><<<grid, 256, 0, stream>>>(static_cast<const AT*>(tok), cls, pos, h, gamma,
-                                                                       beta, eps, static_cast<AT*>(y), I, P)));
+  if (tok_dtype == XS_F32) {
+    XS_DISPATCH_AT(dtype, (embed_ln_kernel<AT, float><<<grid, 256, 0, stream>>>(
+                              static_cast<const float*>(tok), cls, pos, h, gamma, beta, eps, static_cast<AT*>(y), I, P)));
+  } else if (tok_dtype == XS_BF16) {
+    XS_DISPATCH_AT(dtype, (embed_ln_kernel<AT, __nv_bfloat16><<<grid, 256, 0, stream>>>(
+                              static_cast<const __nv_bfloat16*>(tok), cls, pos, h, gamma, beta, eps,
+                              static_cast<AT*>(y), I, P)));
+  } else {
+    set_last_error("embed_ln: unknown tok_dtype %d", tok_dtype);
+    return -1;
+  }
   XS_LAUNCH_CHECK();
   return 0;
 }

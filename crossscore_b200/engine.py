@@ -18,12 +18,13 @@ Data layout in HBM (C = 384, P = patches/image, T = P + 1, I = images in the bat
 from __future__ import annotations
 
 import math
+from contextlib import contextmanager
 from typing import Dict, Optional
 
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, call
+from ._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, DT_TF32, call
 
 C = 384
 PATCH = 14
@@ -34,6 +35,12 @@ NUM_SMS_HINT = 148
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
+
+
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest fp32 -> TF32 (10-bit mantissa); the tensor core itself would truncate."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 class PackedWeights:
@@ -48,12 +55,12 @@ class PackedWeights:
         self.device = device
         f32 = lambda k: sd[k].detach().to(device=device, dtype=torch.float32).contiguous()
         W = lambda t: t.to(self.wdtype).contiguous()
+        # weights of the TF32 GEMMs (patch embed, decoder projections / FFN, head) stay fp32, pre-rounded
+        WP = (lambda t: round_tf32(t.float())) if precision == "bf16" else W
         b = "backbone."
-        # --- patch embed: Conv2d weight (384,3,14,14) -> (384, 588) [c, ky, kx], K zero-padded to 592 for TMA
+        # --- patch embed: Conv2d weight (384,3,14,14) -> (384, 588) [c, ky, kx]
         wpe = f32(b + "embeddings.patch_embeddings.projection.weight").reshape(C, 588)
-        if precision == "bf16":
-            wpe = torch.nn.functional.pad(wpe, (0, 4))
-        self.w_pe, self.b_pe = W(wpe), f32(b + "embeddings.patch_embeddings.projection.bias")
+        self.w_pe, self.b_pe = WP(wpe), f32(b + "embeddings.patch_embeddings.projection.bias")
         self.cls = f32(b + "embeddings.cls_token").reshape(C)
         self.pos = f32(b + "embeddings.position_embeddings")[0].contiguous()  # (1+37*37, C)
         self.layers = []
@@ -100,16 +107,16 @@ class PackedWeights:
             D = {}
             if do_self_attn:
                 wi, bi = f32(p + "self_attn.in_proj_weight"), f32(p + "self_attn.in_proj_bias")
-                D["sa_win"] = W(torch.cat([pad_heads(wi[i * C:(i + 1) * C]) for i in range(3)], 0))
+                D["sa_win"] = WP(torch.cat([pad_heads(wi[i * C:(i + 1) * C]) for i in range(3)], 0))
                 D["sa_bin"] = torch.cat([pad_heads_b(bi[i * C:(i + 1) * C]) for i in range(3)], 0).contiguous()
-                D["sa_wo"], D["sa_bo"] = W(f32(p + "self_attn.out_proj.weight")), f32(p + "self_attn.out_proj.bias")
+                D["sa_wo"], D["sa_bo"] = WP(f32(p + "self_attn.out_proj.weight")), f32(p + "self_attn.out_proj.bias")
             wi, bi = f32(p + "multihead_attn.in_proj_weight"), f32(p + "multihead_attn.in_proj_bias")
-            D["ca_wq"], D["ca_bq"] = W(pad_heads(wi[:C])), pad_heads_b(bi[:C]).contiguous()
+            D["ca_wq"], D["ca_bq"] = WP(pad_heads(wi[:C])), pad_heads_b(bi[:C]).contiguous()
             kv_w += [pad_heads(wi[C:2 * C]), pad_heads(wi[2 * C:])]
             kv_b += [pad_heads_b(bi[C:2 * C]), pad_heads_b(bi[2 * C:])]
-            D["ca_wo"], D["ca_bo"] = W(f32(p + "multihead_attn.out_proj.weight")), f32(p + "multihead_attn.out_proj.bias")
-            D["w1"], D["b1"] = W(f32(p + "linear1.weight")), f32(p + "linear1.bias")
-            D["w2"], D["b2"] = W(f32(p + "linear2.weight")), f32(p + "linear2.bias")
+            D["ca_wo"], D["ca_bo"] = WP(f32(p + "multihead_attn.out_proj.weight")), f32(p + "multihead_attn.out_proj.bias")
+            D["w1"], D["b1"] = WP(f32(p + "linear1.weight")), f32(p + "linear1.bias")
+            D["w2"], D["b2"] = WP(f32(p + "linear2.weight")), f32(p + "linear2.bias")
             for n in (1, 2, 3):
                 D[f"ln{n}_g"], D[f"ln{n}_b"] = f32(p + f"norm{n}.weight"), f32(p + f"norm{n}.bias")
             self.dec.append(D)
@@ -117,12 +124,12 @@ class PackedWeights:
         self.kv_w, self.kv_b = W(torch.cat(kv_w, 0)), torch.cat(kv_b, 0).contiguous()
         self.E = E
         # --- head
-        self.h0_w, self.h0_b = W(f32("ref_cross.head.0.weight")), f32("ref_cross.head.0.bias")
+        self.h0_w, self.h0_b = WP(f32("ref_cross.head.0.weight")), f32("ref_cross.head.0.bias")
         h2w, h2b = f32("ref_cross.head.2.weight"), f32("ref_cross.head.2.bias")
         if precision == "bf16":  # rows padded 196 -> 224 (one tcgen05 N tile)
             h2w = torch.nn.functional.pad(h2w, (0, 0, 0, 28))
             h2b = torch.nn.functional.pad(h2b, (0, 28))
-        self.h2_w, self.h2_b = W(h2w), h2b.contiguous()
+        self.h2_w, self.h2_b = WP(h2w), h2b.contiguous()
         self._tables = {}
 
     # resampled tables are cached per patch grid
@@ -162,6 +169,21 @@ class Engine:
         self.do_self_attn, self.do_short_cut = do_self_attn, do_short_cut
         self.use_tanh, self.power = bool(use_tanh), float(power)
         self._ws = {}
+        self.prof = None  # list of (tag, algorithmic flops, algorithmic bytes, start event, stop event) when profiling
+
+    @contextmanager
+    def _op(self, tag, flops=0.0, nbytes=0.0, launches=1):
+        """Counts kernel launches; when self.prof is a list also brackets the op with CUDA events on the
+        launching stream (used by bench.py for the per-kernel roofline, outside the timed steps)."""
+        _lib.count_launch(launches)
+        if self.prof is None:
+            yield
+            return
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.prof.append((tag, float(flops), float(nbytes), s, e))
 
     # ---- scratch -----------------------------------------------------------------------------
     def _buf(self, name, shape, dtype):
@@ -176,39 +198,55 @@ class Engine:
         return cur[:n].view(*shape)
 
     # ---- thin op wrappers ----------------------------------------------------------------------
-    def _gemm(self, A, Wt, bias, out, act, st):
+    def _gemm(self, A, Wt, bias, out, act, st, tag="gemm", n_real=None, k_real=None):
+        """out = act(A @ Wt^T + bias).  Operand mode follows the tensors: bf16 x bf16 -> tcgen05 kind::f16;
+        fp32 x fp32 -> TF32 tensor cores in the bf16 product mode, SIMT FMA in the fp32 parity mode."""
         M, K = A.shape
         N = Wt.shape[0]
-        call("xs_gemm_bias_act", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(out), out.stride(0),
-             M, N, K, act, self.dt, st)
-        _lib.count_launch()
+        assert A.dtype == Wt.dtype, (A.dtype, Wt.dtype)
+        if A.dtype == torch.bfloat16:
+            dt = DT_BF16
+        else:
+            dt = DT_TF32 if self.dt == DT_BF16 else DT_F32
+        odt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
+        flops = 2.0 * M * (n_real or N) * (k_real or K)  # algorithmic: padding is not counted
+        with self._op(tag, flops):
+            call("xs_gemm_bias_act", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(out),
+                 out.stride(0), M, N, K, act, dt, odt, st)
 
     def _ln(self, res_in, delta, res_out, g, b, eps, y, y32, rows, st):
-        call("xs_layernorm", _ptr(res_in), _ptr(delta), _ptr(res_out), _ptr(g), _ptr(b), eps, _ptr(y), _ptr(y32),
-             rows, self.dt, st)
-        _lib.count_launch()
+        dt = DT_BF16 if (delta is not None and delta.dtype == torch.bfloat16) or \
+            (y is not None and y.dtype == torch.bfloat16) else DT_F32
+        nb = sum(t.element_size() * rows * C for t in (res_in, delta, res_out, y, y32) if t is not None)
+        with self._op("layernorm", 0.0, nb):
+            call("xs_layernorm", _ptr(res_in), _ptr(delta), _ptr(res_out), _ptr(g), _ptr(b), eps, _ptr(y), _ptr(y32),
+                 rows, dt, st)
 
     def _attn(self, q, k, v, o, B, heads, Lq, Lk, d, slot, q_rs, q_bs, kv_rs, kv_bs, kv_shared, st,
               lse=None, name="att"):
-        """q/k/v are tensor views whose data_ptr is the first column of the respective part."""
+        """q/k/v are tensor views whose data_ptr is the first column of the respective part; o is bf16 or
+        fp32 (B*Lq, heads*d)."""
         scale = 1.0 / math.sqrt(d)
         ctas = B * heads * ((Lq + 127) // 128)
         nblk = (Lk + 127) // 128
         nsplit = max(1, min((2 * NUM_SMS_HINT) // max(ctas, 1), nblk // 4))
         per = -(-nblk // nsplit)
         nsplit = -(-nblk // per)  # every split owns at least one key block
+        o_is_f32 = 1 if o.dtype == torch.float32 else 0
+        flops = 4.0 * B * heads * Lq * Lk * d  # QK^T + PV
         if nsplit == 1:
-            o_is_f32 = 1 if self.dt == DT_F32 else 0
-            call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, Lq, Lk, d, slot,
-                 q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), 1, o_is_f32, scale, self.dt, st)
-            _lib.count_launch()
+            with self._op("attn_" + name, flops):
+                call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, Lq, Lk, d, slot,
+                     q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), 1, o_is_f32, scale, self.dt, st)
         else:  # small batch: split the keys across CTAs, then merge (same merge as the multi-GPU path)
             o_parts = self._buf(name + "_oparts", (nsplit, B * Lq, heads * d), torch.float32)
             l_parts = self._buf(name + "_lparts", (nsplit, B, heads, Lq), torch.float32)
-            call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o_parts), _ptr(l_parts), B, heads, Lq, Lk, d, slot,
-                 q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), nsplit, 1, scale, self.dt, st)
-            call("xs_lse_merge", _ptr(o_parts), _ptr(l_parts), _ptr(o), _ptr(lse), nsplit, B, Lq, heads, d, self.dt, st)
-            _lib.count_launch(2)
+            with self._op("attn_" + name, flops):
+                call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o_parts), _ptr(l_parts), B, heads, Lq, Lk, d,
+                     slot, q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), nsplit, 1, scale, self.dt, st)
+            with self._op("lse_merge", 0.0, o_parts.numel() * 4.0):
+                call("xs_lse_merge", _ptr(o_parts), _ptr(l_parts), _ptr(o), _ptr(lse), nsplit, B, Lq, heads, d,
+                     DT_F32 if o_is_f32 else DT_BF16, st)
 
     # ---- DINOv2 backbone over a list of image tensors (each (n,3,H,W) fp32, same H,W) --------------
     def backbone(self, image_groups, st):
@@ -221,16 +259,17 @@ class Engine:
         I = sum(int(g.shape[0]) for g in image_groups)
         pos, _ = w.tables(ph, pw, st)
         A = self.adtype
-        tok = self._buf("tok", (I * P, C), A)
+        pe_dt = DT_TF32 if self.dt == DT_BF16 else DT_F32  # patch embedding: fp32 operands in both modes
+        tok = self._buf("tok", (I * P, C), torch.float32)
         row = 0
         for g in image_groups:
             n = int(g.shape[0])
             assert g.dtype == torch.float32 and g.is_contiguous() and g.shape[1] == 3
-            nbytes = _lib.load().xs_workspace_bytes(_lib.OP_PATCH_EMBED, n, H, Wd, self.dt)
+            nbytes = _lib.load().xs_workspace_bytes(_lib.OP_PATCH_EMBED, n, H, Wd, pe_dt)
             ws = self._buf("im2col", (nbytes,), torch.uint8)
-            call("xs_patch_embed", _ptr(g), _ptr(w.w_pe), _ptr(w.b_pe), _ptr(tok[row * P:]), _ptr(ws), nbytes, n, H, Wd,
-                 self.dt, st)
-            _lib.count_launch(2)
+            with self._op("patch_embed", 2.0 * n * P * 588 * C, launches=2):
+                call("xs_patch_embed", _ptr(g), _ptr(w.w_pe), _ptr(w.b_pe), _ptr(tok[row * P:]), _ptr(ws), nbytes, n, H,
+                     Wd, pe_dt, st)
             row += n
         R = I * T
         h = self._buf("h", (R, C), torch.float32)
@@ -240,17 +279,17 @@ class Engine:
         d = self._buf("d", (R, C), A)
         g1 = self._buf("g", (R, 4 * C), A)
         L0 = w.layers[0]
-        call("xs_embed_cls_pos_ln", _ptr(tok), _ptr(w.cls), _ptr(pos), _ptr(h), _ptr(L0["ln1_g"]), _ptr(L0["ln1_b"]),
-             DINO_EPS, _ptr(y), I, P, self.dt, st)
-        _lib.count_launch()
+        with self._op("embed_ln", 0.0, R * C * (4 + 4 + y.element_size())):
+            call("xs_embed_cls_pos_ln", _ptr(tok), DT_F32, _ptr(w.cls), _ptr(pos), _ptr(h), _ptr(L0["ln1_g"]),
+                 _ptr(L0["ln1_b"]), DINO_EPS, _ptr(y), I, P, self.dt, st)
         for l, L in enumerate(w.layers):
-            self._gemm(y, L["wqkv"], L["bqkv"], qkv, ACT_NONE, st)
+            self._gemm(y, L["wqkv"], L["bqkv"], qkv, ACT_NONE, st, tag="gemm_dino_qkv")
             self._attn(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, I, DINO_HEADS, T, T, 64, 64,
                        3 * C, T * 3 * C, 3 * C, T * 3 * C, False, st, name="dino")
-            self._gemm(att, L["wo"], L["bo"], d, ACT_NONE, st)
+            self._gemm(att, L["wo"], L["bo"], d, ACT_NONE, st, tag="gemm_dino_proj")
             self._ln(h, d, h, L["ln2_g"], L["ln2_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN2(h)
-            self._gemm(y, L["w1"], L["b1"], g1, ACT_GELU, st)
-            self._gemm(g1, L["w2"], L["b2"], d, ACT_NONE, st)
+            self._gemm(y, L["w1"], L["b1"], g1, ACT_GELU, st, tag="gemm_dino_fc1")
+            self._gemm(g1, L["w2"], L["b2"], d, ACT_NONE, st, tag="gemm_dino_fc2")
             if l + 1 < DINO_LAYERS:
                 Ln = w.layers[l + 1]
                 self._ln(h, d, h, Ln["ln1_g"], Ln["ln1_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN1_{l+1}(h)
@@ -258,7 +297,7 @@ class Engine:
 
     def features(self, query_img, ref_imgs, st, want_mem=True):
         """DINOv2 + final LN + CLS drop + PE.  query_img (B,3,H,W) or None, ref_imgs (B,N,3,H,W) or None.
-        Returns xq32 (B*P,C) fp32, xq (B*P,C) AT, mem (B*N*P,C) AT (None where not requested)."""
+        Returns xq32 (B*P,C) fp32 and mem (B*N*P,C) AT (None where not requested)."""
         w = self.w
         groups, nq = [], 0
         if query_img is not None:
@@ -274,41 +313,43 @@ class Engine:
         h, d, I, P = self.backbone(groups, st)
         _, pe = w.tables(ph, pw, st)
         xq32 = self._buf("xq32", (nq * P, C), torch.float32) if nq else None
-        xq = self._buf("xq", (nq * P, C), self.adtype) if nq else None
         mem = self._buf("mem", (nr * P, C), self.adtype) if nr and want_mem else None
-        call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS, _ptr(pe),
-             _ptr(xq32), _ptr(xq), _ptr(mem), I, nq, P, self.dt, st)
-        _lib.count_launch()
-        return xq32, xq, mem
+        with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + 2 * d.element_size())):
+            call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS, _ptr(pe),
+                 _ptr(xq32), None, _ptr(mem), I, nq, P, self.dt, st)
+        return xq32, mem
 
     def project_kv(self, mem, st, out=None):
         """K/V of both decoder layers for reference tokens mem (rows, C) -> (rows, 4E)."""
         rows = mem.shape[0]
         kv = out if out is not None else self._buf("kv", (rows, 4 * self.w.E), self.adtype)
-        self._gemm(mem, self.w.kv_w, self.w.kv_b, kv, ACT_NONE, st)
+        self._gemm(mem, self.w.kv_w, self.w.kv_b, kv, ACT_NONE, st, tag="gemm_dec_kv", n_real=4 * C)
         return kv
 
-    def decode(self, xq32, xq, kv, B, P, M, ph, pw, st, kv_shared=False, need_attn_weights=False, head_id=0,
+    def decode(self, xq32, kv, B, P, M, ph, pw, st, kv_shared=False, need_attn_weights=False, head_id=0,
                cross_attn_fn=None):
-        """2-layer post-norm decoder + head + jigsaw.  kv: (B*M or M, 4E) projected reference K/V.
-        cross_attn_fn (optional) replaces the local cross-attention call (multi-GPU split-KV)."""
+        """2-layer post-norm decoder + head + jigsaw.  xq32 (B*P, C) fp32 decoder stream (updated in place);
+        kv: (B*M or M, 4E) projected reference K/V.  The decoder stream and every GEMM input/output except
+        Q/K/V stay fp32 (TF32 tensor cores in the bf16 product mode): these 2 % of the FLOPs carry half of the
+        bf16 error budget.  cross_attn_fn (optional) replaces the local cross-attention (multi-GPU split-KV)."""
         w, A, E, slot = self.w, self.adtype, self.w.E, self.w.slot
         R = B * P
+        f32 = torch.float32
         qkv_s = self._buf("dec_qkv", (R, 3 * E), A)
         qc = self._buf("dec_q", (R, E), A)
-        att = self._buf("dec_att", (R, C), A)
-        d = self._buf("dec_d", (R, C), A)
-        f = self._buf("dec_f", (R, C), A)
-        lse = self._buf("dec_lse", (B, DEC_HEADS, P), torch.float32) if need_attn_weights else None
+        att = self._buf("dec_att", (R, C), f32)
+        d = self._buf("dec_d", (R, C), f32)
+        f = self._buf("dec_f", (R, C), f32)
+        lse = self._buf("dec_lse", (B, DEC_HEADS, P), f32) if need_attn_weights else None
         sc = self.do_short_cut
         for l, D in enumerate(w.dec):
             if self.do_self_attn:
-                self._gemm(xq, D["sa_win"], D["sa_bin"], qkv_s, ACT_NONE, st)
+                self._gemm(xq32, D["sa_win"], D["sa_bin"], qkv_s, ACT_NONE, st, tag="gemm_dec", n_real=3 * C)
                 self._attn(qkv_s[:, 0:], qkv_s[:, E:], qkv_s[:, 2 * E:], att, B, DEC_HEADS, P, P, DEC_D, slot,
                            3 * E, P * 3 * E, 3 * E, P * 3 * E, False, st, name="dsa")
-                self._gemm(att, D["sa_wo"], D["sa_bo"], d, ACT_NONE, st)
-                self._ln(xq32 if sc else None, d, None, D["ln1_g"], D["ln1_b"], DEC_EPS, xq, xq32, R, st)
-            self._gemm(xq, D["ca_wq"], D["ca_bq"], qc, ACT_NONE, st)
+                self._gemm(att, D["sa_wo"], D["sa_bo"], d, ACT_NONE, st, tag="gemm_dec")
+                self._ln(xq32 if sc else None, d, None, D["ln1_g"], D["ln1_b"], DEC_EPS, None, xq32, R, st)
+            self._gemm(xq32, D["ca_wq"], D["ca_bq"], qc, ACT_NONE, st, tag="gemm_dec", n_real=C)
             k_view, v_view = kv[:, l * 2 * E:], kv[:, l * 2 * E + E:]
             last = need_attn_weights and l == DEC_LAYERS - 1
             if cross_attn_fn is not None:
@@ -316,38 +357,40 @@ class Engine:
             else:
                 self._attn(qc, k_view, v_view, att, B, DEC_HEADS, P, M, DEC_D, slot, E, P * E, 4 * E, M * 4 * E,
                            kv_shared, st, lse=lse if last else None, name="dca")
-            self._gemm(att, D["ca_wo"], D["ca_bo"], d, ACT_NONE, st)
-            self._ln(xq32 if sc else None, d, None, D["ln2_g"], D["ln2_b"], DEC_EPS, xq, xq32, R, st)
-            self._gemm(xq, D["w1"], D["b1"], f, ACT_RELU, st)
-            self._gemm(f, D["w2"], D["b2"], d, ACT_NONE, st)
-            self._ln(xq32, d, None, D["ln3_g"], D["ln3_b"], DEC_EPS, xq, xq32, R, st)
+            self._gemm(att, D["ca_wo"], D["ca_bo"], d, ACT_NONE, st, tag="gemm_dec")
+            self._ln(xq32 if sc else None, d, None, D["ln2_g"], D["ln2_b"], DEC_EPS, None, xq32, R, st)
+            self._gemm(xq32, D["w1"], D["b1"], f, ACT_RELU, st, tag="gemm_dec")
+            self._gemm(f, D["w2"], D["b2"], d, ACT_NONE, st, tag="gemm_dec")
+            self._ln(xq32, d, None, D["ln3_g"], D["ln3_b"], DEC_EPS, None, xq32, R, st)
         probs = None
         if need_attn_weights:
-            if not 0 <= head_id < DEC_HEADS:
-                raise IndexError(f"need_attn_weights_head_id={head_id} out of range for {DEC_HEADS} heads")
-            probs = torch.empty(B, P, M, device=self.device, dtype=torch.float32)
+            probs = torch.empty(B, P, M, device=self.device, dtype=f32)
             l = DEC_LAYERS - 1
-            call("xs_attn_probs_one_head", _ptr(qc), _ptr(kv[:, l * 2 * E:]), _ptr(lse), _ptr(probs), B, DEC_HEADS,
-                 head_id, P, M, DEC_D, slot, E, P * E, 4 * E, 0 if kv_shared else M * 4 * E, 1.0 / math.sqrt(DEC_D),
-                 self.dt, st)
-            _lib.count_launch()
-        self._gemm(xq, w.h0_w, w.h0_b, f, ACT_LEAKY, st)
-        score = torch.empty(B, PATCH * ph, PATCH * pw, device=self.device, dtype=torch.float32)
-        call("xs_head_score_jigsaw", _ptr(f), f.stride(0), _ptr(w.h2_w), w.h2_w.stride(0), _ptr(w.h2_b), _ptr(score), B,
-             ph, pw, C, int(self.use_tanh), self.power, self.dt, st)
-        _lib.count_launch()
+            with self._op("attn_probs", 0.0, probs.numel() * 4.0):
+                call("xs_attn_probs_one_head", _ptr(qc), _ptr(kv[:, l * 2 * E:]), _ptr(lse), _ptr(probs), B, DEC_HEADS,
+                     head_id, P, M, DEC_D, slot, E, P * E, 4 * E, 0 if kv_shared else M * 4 * E,
+                     1.0 / math.sqrt(DEC_D), self.dt, st)
+        self._gemm(xq32, w.h0_w, w.h0_b, f, ACT_LEAKY, st, tag="gemm_dec")
+        score = torch.empty(B, PATCH * ph, PATCH * pw, device=self.device, dtype=f32)
+        # K12 algorithmic bytes: token features in + fp32 score map out
+        with self._op("head_jigsaw", 2.0 * R * C * 196, R * C * f.element_size() + score.numel() * 4.0):
+            call("xs_head_score_jigsaw", _ptr(f), f.stride(0), _ptr(w.h2_w), w.h2_w.stride(0), _ptr(w.h2_b),
+                 _ptr(score), B, ph, pw, C, int(self.use_tanh), self.power,
+                 DT_TF32 if self.dt == DT_BF16 else DT_F32, st)
         return score, probs
 
     # ---- the reference-shaped forward ------------------------------------------------------------
     def forward(self, query_img, ref_imgs, need_attn_weights=False, head_id=0):
+        if need_attn_weights and not 0 <= head_id < DEC_HEADS:
+            raise IndexError(f"need_attn_weights_head_id={head_id} out of range for {DEC_HEADS} heads")
         st = torch.cuda.current_stream(self.device).cuda_stream
         B, _, H, Wd = query_img.shape
         N = ref_imgs.shape[1]
         ph, pw = H // PATCH, Wd // PATCH
         P = ph * pw
-        xq32, xq, mem = self.features(query_img, ref_imgs, st)
+        xq32, mem = self.features(query_img, ref_imgs, st)
         kv = self.project_kv(mem, st)
-        score, probs = self.decode(xq32, xq, kv, B, P, N * P, ph, pw, st, kv_shared=False,
+        score, probs = self.decode(xq32, kv, B, P, N * P, ph, pw, st, kv_shared=False,
                                    need_attn_weights=need_attn_weights, head_id=head_id)
         if probs is not None:
             probs = probs.view(B, ph, pw, N, ph, pw)

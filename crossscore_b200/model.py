@@ -132,7 +132,7 @@ class CrossScoreNet(nn.Module):
             pos, _ = eng.w.tables(H // 14, W // 14, st)
             eng.w._tables[(H // 14, W // 14)] = (pos, torch.zeros(P, 384, device=query_img.device))
             refs = None if ref_cross_imgs is None else ref_cross_imgs.contiguous()
-            xq32, _, mem = eng.features(query_img.contiguous(), refs, st)
+            xq32, mem = eng.features(query_img.contiguous(), refs, st)
             out = {"query": xq32.view(B, P, 384).clone(),
                    "ref_cross": None if mem is None else mem.float().view(B, -1, 384).clone()}
         finally:

@@ -15,8 +15,11 @@
  *     memory (PyTorch caching allocator in the shipped host code); kernels are enqueued on `stream`
  *     (a cudaStream_t) with no implicit synchronisation and are CUDA-graph capturable.
  *   - dtype selects the activation storage: XS_DTYPE_BF16 (tcgen05 tensor-core path) or
- *     XS_DTYPE_F32 (fp32 parity mode, SIMT).  Statistics, residual stream, tables, biases and the score
- *     map are always fp32.  Hidden size is 384 (DINOv2-small) throughout.
+ *     XS_DTYPE_F32 (fp32 parity mode, SIMT).  The GEMM-type entries also accept XS_DTYPE_TF32: fp32
+ *     operands multiplied as TF32 on the tensor cores (the bf16 product mode uses it for the ~2 % of FLOPs
+ *     that dominate the bf16 error budget: patch embedding, decoder projections/FFN, head).
+ *     Statistics, residual stream, tables, biases and the score map are always fp32.  Hidden size is 384
+ *     (DINOv2-small) throughout.
  *   - bf16 attention operands use 64-column head slots: head h of a row lives at columns
  *     [h*64, h*64+head_dim); for head_dim 48 (decoder) the projection weights are padded so the 16
  *     trailing columns of each slot are never read.
@@ -35,6 +38,7 @@ extern "C" {
 
 #define XS_DTYPE_BF16 0
 #define XS_DTYPE_F32 1
+#define XS_DTYPE_TF32 2 /* GEMM operand mode only: fp32 in memory, multiplied as TF32 on the tensor cores */
 
 #define XS_ACT_NONE 0
 #define XS_ACT_GELU 1  /* exact (erf) GELU: Dinov2MLP, $SP/transformers/models/dinov2/modeling_dinov2.py:312-328 */
@@ -54,14 +58,15 @@ size_t xs_workspace_bytes(int op, int a, int b, int c, int dtype);
 
 /* K1  Dinov2PatchEmbeddings.projection: Conv2d(3,384,k=14,s=14) == im2col + GEMM
  *     ($SP/transformers/models/dinov2/modeling_dinov2.py:139-149).
- *     img (I,3,H,W) fp32;  w: bf16 (384,592) zero-padded K / fp32 (384,588);  tok (I*P,384). */
+ *     img (I,3,H,W) fp32;  w: bf16 (384,592) zero-padded K / fp32 (384,588) for F32 and TF32;
+ *     tok (I*P,384) bf16 for BF16, fp32 for F32 and TF32. */
 int xs_patch_embed(const float* img, const void* w, const float* bias, void* tok, void* workspace,
                    size_t workspace_bytes, int n_images, int H, int W, int dtype, xs_stream_t stream);
 
 /* K1b CLS cat + position embedding add (modeling_dinov2.py:108-112) fused with layer-0 norm1 (:354,371).
  *     h (I*(P+1),384) fp32 residual stream out;  y = LN(h) in activation dtype. */
-int xs_embed_cls_pos_ln(const void* tok, const float* cls, const float* pos, float* h, const float* gamma,
-                        const float* beta, float eps, void* y, int n_images, int P, int dtype,
+int xs_embed_cls_pos_ln(const void* tok, int tok_dtype, const float* cls, const float* pos, float* h,
+                        const float* gamma, const float* beta, float eps, void* y, int n_images, int P, int dtype,
                         xs_stream_t stream);
 
 /* K2  LayerNorm with fused residual add: x = res_in + delta;  res_out = x (optional);
@@ -88,9 +93,11 @@ int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw
                                   xs_stream_t stream);
 
 /* K3,K5-K7,K9-K11  out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N])   (torch.nn.Linear everywhere on the path)
- *     bf16: N multiple of 192 or 256, K/lda/ldw/ldc multiples of 8.  fp32: any shape, lda/ldw % 4 == 0. */
+ *     dtype = operand type (BF16 / TF32 tensor cores, F32 SIMT); out_dtype = BF16 or F32.
+ *     Tensor-core modes: N multiple of 192 or 256, row pitches multiples of 16 bytes; bf16->fp32 and
+ *     tf32->bf16 support act NONE only.  fp32: any shape, lda/ldw % 4 == 0, fp32 output. */
 int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc,
-                     int M, int N, int K, int act, int dtype, xs_stream_t stream);
+                     int M, int N, int K, int act, int dtype, int out_dtype, xs_stream_t stream);
 
 /* K4,K9,K10  O = softmax(Q K^T * scale) V  per (batch, head), no mask
  *     (modeling_dinov2.py:203-234; $SP/torch/nn/functional.py:6630-6692 via transformer.py:182-205).
@@ -110,7 +117,8 @@ int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float*
 
 /* K12  head[2] Linear(384->196) + Sigmoid/Tanh (+pow) + jigsaw_to_image
  *      (model/cross_reference.py:45-50,82-87; model/regression_layer.py:26-62; utils/misc/image.py:8-21).
- *      A (B*ph*pw, 384);  W: bf16 (224,384) zero-padded rows / fp32 (196,384);  score (B,14ph,14pw) fp32. */
+ *      A (B*ph*pw, 384);  W: (224,384) zero-padded rows for BF16 / TF32, fp32 (196,384) for F32;
+ *      score (B,14ph,14pw) fp32. */
 int xs_head_score_jigsaw(const void* A, int lda, const void* W, int ldw, const float* bias, float* score, int B,
                          int ph, int pw, int K, int use_tanh, float power, int dtype, xs_stream_t stream);
 

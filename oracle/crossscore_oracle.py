@@ -23,6 +23,12 @@ from typing import Dict, Optional
 
 import torch
 
+# FAST = True switches the three heaviest primitives to torch's fused CPU ops (F.scaled_dot_product_attention,
+# F.layer_norm, F.gelu) -- the very library calls the reference makes on CPU -- so that the timed CPU
+# baseline reflects the reference's real CPU speed rather than the spelled-out restatement's.  The
+# spelled-out path (FAST = False, the default) is the parity checker; tests pin both against the goldens.
+FAST = False
+
 PATCH = 14
 HIDDEN = 384
 DINO_HEADS = 6
@@ -39,6 +45,8 @@ DINO_GRID = 37  # 518 // 14, the pre-trained position-embedding grid
 # ----------------------------------------------------------------------------------------
 def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
     """LayerNorm over the last dim, biased variance (torch.nn.LayerNorm semantics)."""
+    if FAST:
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
     mu = x.mean(dim=-1, keepdim=True)
     var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + eps) * w + b
@@ -51,6 +59,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch
 
 def gelu_erf(x: torch.Tensor) -> torch.Tensor:
     """Exact GELU ($SP/transformers/models/dinov2/modeling_dinov2.py:312-328, hidden_act="gelu")."""
+    if FAST:
+        return torch.nn.functional.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
@@ -75,6 +85,9 @@ def mha(q_in, k_in, v_in, w_in, b_in, w_out, b_out, n_heads, return_probs=False)
     q = q.view(B, Lq, n_heads, d).transpose(1, 2)
     k = k.view(B, Lk, n_heads, d).transpose(1, 2)
     v = v.view(B, Lk, n_heads, d).transpose(1, 2)
+    if FAST and not return_probs:
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, Lq, E)
+        return linear(o, w_out, b_out), None
     s = (q @ k.transpose(-1, -2)) / math.sqrt(d)
     p = softmax_rows(s)
     o = (p @ v).transpose(1, 2).reshape(B, Lq, E)
@@ -201,7 +214,10 @@ def dinov2_features(sd: Dict[str, torch.Tensor], imgs: torch.Tensor, dt=torch.fl
         q = q.view(I, T, DINO_HEADS, d).transpose(1, 2)
         k = k.view(I, T, DINO_HEADS, d).transpose(1, 2)
         v = v.view(I, T, DINO_HEADS, d).transpose(1, 2)
-        a = softmax_rows((q @ k.transpose(-1, -2)) / math.sqrt(d)) @ v
+        if FAST:
+            a = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        else:
+            a = softmax_rows((q @ k.transpose(-1, -2)) / math.sqrt(d)) @ v
         a = a.transpose(1, 2).reshape(I, T, HIDDEN)
         a = linear(a, g(p + "attention.output.dense.weight"), g(p + "attention.output.dense.bias"))
         h = h + g(p + "layer_scale1.lambda1") * a

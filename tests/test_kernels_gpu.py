@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from crossscore_b200 import _lib
-from crossscore_b200._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, call
+from crossscore_b200._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, DT_TF32, call
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -54,7 +54,7 @@ def test_library_and_device():
 def test_gemm_f32(M, N, K, act):
     A, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
     out = torch.empty(M, N, device=DEV)
-    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_F32, st())
+    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_F32, DT_F32, st())
     ref = act_ref(A.double() @ W.double().T + b.double(), act)
     assert (out.double() - ref).abs().max() < 2e-5
 
@@ -76,7 +76,7 @@ def test_gemm_bf16_tc(M, N, K, act):
     W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
     b = rnd(N, seed=3)
     out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
-    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_BF16, st())
+    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_BF16, DT_BF16, st())
     torch.cuda.synchronize()
     ref = act_ref(A.float() @ W.float().T + b, act)
     err = (out.float() - ref).abs()
@@ -86,13 +86,49 @@ def test_gemm_bf16_tc(M, N, K, act):
     assert err.mean() < 5e-3
 
 
+@pytest.mark.parametrize("M,N,K,act,out_bf16", [
+    (128, 192, 32, ACT_NONE, False),     # one tile, one k-block
+    (300, 384, 384, ACT_NONE, False),    # decoder out-proj / linear2
+    (1369, 384, 384, ACT_RELU, False),   # linear1
+    (1369, 384, 384, ACT_LEAKY, False),  # head.0
+    (2738, 384, 588, ACT_NONE, False),   # patch embedding: K tail block zero-filled by TMA
+    (1369, 1536, 384, ACT_NONE, True),   # decoder self-attention in-proj -> bf16 q|k|v
+    (1369, 512, 384, ACT_NONE, True),    # cross-attention q-proj
+    (30000, 384, 384, ACT_NONE, False),  # persistent loop
+])
+def test_gemm_tf32_tc(M, N, K, act, out_bf16):
+    A, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=odt)
+    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, act, DT_TF32,
+         DT_BF16 if out_bf16 else DT_F32, st())
+    torch.cuda.synchronize()
+    ref = act_ref(A.double() @ W.double().T + b.double(), act)
+    err = (out.double() - ref).abs()
+    assert torch.isfinite(out.float()).all()
+    tol = (0.02 + 0.01 * ref.abs()) if out_bf16 else (3e-3 + 2e-3 * ref.abs())
+    assert (err <= tol).all(), f"max err {err.max().item()}"
+    assert err.mean() < (5e-3 if out_bf16 else 8e-4)
+
+
+def test_gemm_bf16_in_f32_out():
+    M, N, K = 1000, 384, 1536
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+    b = rnd(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, ACT_NONE, DT_BF16, DT_F32, st())
+    ref = A.double() @ W.double().T + b.double()
+    assert (out.double() - ref).abs().max() < 2e-3
+
+
 def test_gemm_bf16_rejects_bad_shapes():
     A = rnd(128, 384, dtype=torch.bfloat16)
     W = rnd(200, 384, dtype=torch.bfloat16)
     b = rnd(200)
     out = torch.empty(128, 200, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(_lib.XsError):
-        call("xs_gemm_bias_act", P(A), 384, P(W), 384, P(b), P(out), 200, 128, 200, 384, ACT_NONE, DT_BF16, st())
+        call("xs_gemm_bias_act", P(A), 384, P(W), 384, P(b), P(out), 200, 128, 200, 384, ACT_NONE, DT_BF16, DT_BF16, st())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -105,22 +141,24 @@ def attn_ref(q, k, v, scale):
     return torch.softmax(s, -1) @ v, lse
 
 
-def run_attn(dtype_flag, B, H, Lq, Lk, d, slot, nsplit=1, kv_shared=False, seed=0, qscale=1.0):
+def run_attn(dtype_flag, B, H, Lq, Lk, d, slot, nsplit=1, kv_shared=False, seed=0, qscale=1.0, force_f32_out=False):
     adt = torch.bfloat16 if dtype_flag == DT_BF16 else torch.float32
     Bkv = 1 if kv_shared else B
     q = rnd(B, Lq, H * slot, seed=seed, scale=qscale, dtype=adt)
     k = rnd(Bkv, Lk, H * slot, seed=seed + 1, dtype=adt)
     v = rnd(Bkv, Lk, H * slot, seed=seed + 2, dtype=adt)
     scale = 1.0 / math.sqrt(d)
-    o_f32 = 1 if (dtype_flag == DT_F32 or nsplit > 1) else 0
+    o_f32 = 1 if (dtype_flag == DT_F32 or nsplit > 1 or force_f32_out) else 0
     o = torch.full((nsplit, B * Lq, H * d), float("nan"), device=DEV, dtype=torch.float32 if o_f32 else adt)
     lse = torch.full((nsplit, B, H, Lq), float("nan"), device=DEV)
     call("xs_flash_attn", P(q), P(k), P(v), P(o), P(lse), B, H, Lq, Lk, d, slot, H * slot, Lq * H * slot, H * slot,
          Lk * H * slot, int(kv_shared), nsplit, o_f32, scale, dtype_flag, st())
     if nsplit > 1:
-        merged = torch.empty(B * Lq, H * d, device=DEV, dtype=adt)
+        mdt = torch.float32 if force_f32_out else adt
+        merged = torch.empty(B * Lq, H * d, device=DEV, dtype=mdt)
         lse_m = torch.empty(B, H, Lq, device=DEV)
-        call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d, dtype_flag, st())
+        call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d,
+             DT_F32 if mdt == torch.float32 else DT_BF16, st())
         o, lse = merged, lse_m
     else:
         o, lse = o[0], lse[0]
@@ -164,6 +202,14 @@ def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale):
     assert (lse - lse_ref).abs().max() < 0.02
 
 
+@pytest.mark.parametrize("nsplit", [1, 2])
+def test_flash_attn_bf16_tc_f32_out(nsplit):
+    """decoder configuration: bf16 q/k/v, fp32 attention output (feeds the TF32 out-proj GEMM)"""
+    o, ref, lse, lse_ref = run_attn(DT_BF16, 2, 8, 300, 1400, 48, 64, nsplit, False, force_f32_out=True)
+    err = (o - ref).abs()
+    assert err.max() < 0.03 and err.mean() < 3e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------
@@ -186,36 +232,42 @@ def test_layernorm_residual(dt):
     assert (y.double() - ref2).abs().max() < (1e-5 if dt == DT_F32 else 0.04)
 
 
-@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
-def test_patch_embed_embed_final(dt):
-    from oracle import crossscore_oracle as O
-    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+@pytest.mark.parametrize("pe_dt", [DT_F32, DT_TF32, DT_BF16])
+def test_patch_embed(pe_dt):
     I, H, W = 3, 84, 117
     ph, pw = H // 14, W // 14
     Pn = ph * pw
     img = rnd(I, 3, H, W, seed=5)
     wconv = rnd(384, 3, 14, 14, seed=6, scale=0.05)
     bias = rnd(384, seed=7, scale=0.1)
-    K = 592 if dt == DT_BF16 else 588
+    tdt = torch.bfloat16 if pe_dt == DT_BF16 else torch.float32
+    K = 592 if pe_dt == DT_BF16 else 588
     w2 = wconv.reshape(384, 588)
-    if dt == DT_BF16:
+    if pe_dt == DT_BF16:
         w2 = torch.nn.functional.pad(w2, (0, 4))
-    w2 = w2.to(adt).contiguous()
-    nbytes = _lib.load().xs_workspace_bytes(_lib.OP_PATCH_EMBED, I, H, W, dt)
-    assert nbytes == I * Pn * K * (2 if dt == DT_BF16 else 4)
+    w2 = w2.to(tdt).contiguous()
+    nbytes = _lib.load().xs_workspace_bytes(_lib.OP_PATCH_EMBED, I, H, W, pe_dt)
+    assert nbytes == I * Pn * K * (2 if pe_dt == DT_BF16 else 4)
     ws = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
-    tok = torch.empty(I * Pn, 384, device=DEV, dtype=adt)
-    call("xs_patch_embed", P(img), P(w2), P(bias), P(tok), P(ws), nbytes, I, H, W, dt, st())
+    tok = torch.full((I * Pn, 384), float("nan"), device=DEV, dtype=tdt)
+    call("xs_patch_embed", P(img), P(w2), P(bias), P(tok), P(ws), nbytes, I, H, W, pe_dt, st())
     ref = torch.nn.functional.conv2d(img.double(), wconv.double(), bias.double(), stride=14).flatten(2).transpose(1, 2)
-    tol = 1e-4 if dt == DT_F32 else 0.06
+    tol = {DT_F32: 1e-4, DT_TF32: 6e-3, DT_BF16: 0.06}[pe_dt]
     assert (tok.double().view(I, Pn, 384) - ref).abs().max() < tol
+
+
+@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
+def test_embed_and_final_ln(dt):
+    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+    I, Pn = 3, 48
+    tok = rnd(I * Pn, 384, seed=10)
 
     # embeddings + first LN
     cls, pos = rnd(384, seed=8), rnd(Pn + 1, 384, seed=9, scale=0.3)
     g, b = rnd(384, seed=3) * 0.2 + 1, rnd(384, seed=4, scale=0.1)
     h = torch.empty(I * (Pn + 1), 384, device=DEV)
     y = torch.empty(I * (Pn + 1), 384, device=DEV, dtype=adt)
-    call("xs_embed_cls_pos_ln", P(tok), P(cls), P(pos), P(h), P(g), P(b), 1e-6, P(y), I, Pn, dt, st())
+    call("xs_embed_cls_pos_ln", P(tok), DT_F32, P(cls), P(pos), P(h), P(g), P(b), 1e-6, P(y), I, Pn, dt, st())
     href = torch.cat([cls.double().expand(I, 1, 384), tok.double().view(I, Pn, 384)], 1) + pos.double()[None]
     assert (h.double().view(I, Pn + 1, 384) - href).abs().max() < 1e-5
     yref = torch.nn.functional.layer_norm(href, (384,), g.double(), b.double(), 1e-6)

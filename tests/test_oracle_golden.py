@@ -40,6 +40,19 @@ def test_oracle_matches_reference_518_fp32():
     assert mx < 1e-4 and mean < 1e-5, (mx, mean)
 
 
+def test_fast_cpu_variant_matches_reference():
+    """bench.py times the oracle with torch's fused CPU ops (O.FAST); same results as the spelled-out path."""
+    rec = load_golden("g2_nonsquare_84x117_n3_attn")
+    sd, q, r = golden_problem(rec)
+    O.FAST = True
+    try:
+        out = O.crossscore_forward(sd, q, r, dt=torch.float32)
+    finally:
+        O.FAST = False
+    mx, mean = compare_to_golden(out["score_map_ref_cross"], rec)
+    assert mx < 1e-4 and mean < 1e-5, (mx, mean)
+
+
 def test_resamplers_match_torch_interpolate():
     """The spelled-out bicubic / bilinear restatements equal F.interpolate (the library call
     the reference makes: positional_encoding.py:61-69, modeling_dinov2.py:86-91)."""

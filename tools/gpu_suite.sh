@@ -11,10 +11,10 @@ run_group () {  # file, -k expression, log name
   echo "[$3] exit $? : $(tail -n 1 gpurun_out/$3.log)"
 }
 if [ "$what" = "kernels" ] || [ "$what" = "all" ]; then
-  for t in test_library_and_device test_gemm_f32 test_gemm_bf16_tc test_gemm_bf16_rejects test_flash_attn_f32 \
-           test_flash_attn_bf16_tc test_layernorm_residual test_patch_embed_embed_final test_table_resamplers \
+  for t in test_library_and_device test_gemm_f32 test_gemm_bf16_tc test_gemm_tf32_tc test_gemm_bf16_in_f32_out test_gemm_bf16_rejects test_flash_attn_f32 \
+           "test_flash_attn_bf16_tc and not f32_out" test_flash_attn_bf16_tc_f32_out test_layernorm_residual test_patch_embed test_embed_and_final_ln test_table_resamplers \
            test_head_score_jigsaw test_attn_probs_one_head; do
-    run_group tests/test_kernels_gpu.py "$t" "k_$t"
+    run_group tests/test_kernels_gpu.py "$t" "k_$(echo $t | tr ' ' '_')"
   done
 fi
 if [ "$what" = "model" ] || [ "$what" = "all" ]; then
