@@ -38,6 +38,86 @@ struct AttnParams {
   float scale_log2;
 };
 
+// ---- softmax building blocks (thread == query row; S row = 128 fp32 TMEM columns at t_s) -------------------
+template <bool MASKED>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int col0, int valid) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    if constexpr (MASKED) {
+      m0 = fmaxf(m0, (col0 + i + 0 < valid) ? __uint_as_float(v[i + 0]) : -INFINITY);
+      m1 = fmaxf(m1, (col0 + i + 1 < valid) ? __uint_as_float(v[i + 1]) : -INFINITY);
+      m2 = fmaxf(m2, (col0 + i + 2 < valid) ? __uint_as_float(v[i + 2]) : -INFINITY);
+      m3 = fmaxf(m3, (col0 + i + 3 < valid) ? __uint_as_float(v[i + 3]) : -INFINITY);
+    } else {
+      m0 = fmaxf(m0, __uint_as_float(v[i + 0]));
+      m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+      m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+      m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// raw (unscaled) row max over the 128 columns; the TMEM load of chunk c+1 is in flight while chunk c is reduced
+template <bool MASKED>
+__device__ __forceinline__ float row_max_pass(uint32_t t_s, int valid) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(t_s, va);
+  tmem_ld_wait32(va);
+  tmem_ld32(t_s + 32, vb);
+  float mx = chunk_max<MASKED>(va, 0, valid);
+  tmem_ld_wait32(vb);
+  tmem_ld32(t_s + 64, va);
+  mx = fmaxf(mx, chunk_max<MASKED>(vb, 32, valid));
+  tmem_ld_wait32(va);
+  tmem_ld32(t_s + 96, vb);
+  mx = fmaxf(mx, chunk_max<MASKED>(va, 64, valid));
+  tmem_ld_wait32(vb);
+  return fmaxf(mx, chunk_max<MASKED>(vb, 96, valid));
+}
+
+// P = exp2(S*sl2 - m) for 32 columns -> 16 packed bf16 pairs stored to TMEM at t_dst; returns the partial row sum
+template <bool MASKED>
+__device__ __forceinline__ float chunk_exp_store(const uint32_t (&v)[32], uint32_t t_dst, float sl2, float m, int col0,
+                                                 int valid) {
+  uint32_t pk[16];
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m));
+    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m));
+    if constexpr (MASKED) {
+      p0 = (col0 + 2 * i < valid) ? p0 : 0.f;
+      p1 = (col0 + 2 * i + 1 < valid) ? p1 : 0.f;
+    }
+    l0 += p0;
+    l1 += p1;
+    pk[i] = pack_bf16x2(p0, p1);
+  }
+  tmem_st16(t_dst, pk);
+  return l0 + l1;
+}
+
+// second pass over the S row; P overwrites the S columns already consumed (P cols [16c,16c+16) <= S cols < 32c+32)
+template <bool MASKED>
+__device__ __forceinline__ float row_exp_pass(uint32_t t_s, float sl2, float m, int valid) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(t_s, va);
+  tmem_ld_wait32(va);
+  tmem_ld32(t_s + 32, vb);
+  float l = chunk_exp_store<MASKED>(va, t_s, sl2, m, 0, valid);
+  tmem_ld_wait32(vb);
+  tmem_ld32(t_s + 64, va);
+  l += chunk_exp_store<MASKED>(vb, t_s + 16, sl2, m, 32, valid);
+  tmem_ld_wait32(va);
+  tmem_ld32(t_s + 96, vb);
+  l += chunk_exp_store<MASKED>(va, t_s + 32, sl2, m, 64, valid);
+  tmem_ld_wait32(vb);
+  l += chunk_exp_store<MASKED>(vb, t_s + 48, sl2, m, 96, valid);
+  return l;
+}
+
 template <int DQK_STEPS, int DV>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -153,24 +233,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       const int valid = kv_end - (kv_begin + j * 128);  // columns >= valid are past the sequence end
 
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tc_wait_ld();
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const int col = c * 32 + i;
-          m0 = fmaxf(m0, (col + 0 < valid) ? __uint_as_float(v[i + 0]) : -INFINITY);
-          m1 = fmaxf(m1, (col + 1 < valid) ? __uint_as_float(v[i + 1]) : -INFINITY);
-          m2 = fmaxf(m2, (col + 2 < valid) ? __uint_as_float(v[i + 2]) : -INFINITY);
-          m3 = fmaxf(m3, (col + 3 < valid) ? __uint_as_float(v[i + 3]) : -INFINITY);
-        }
-        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      }
+      // ---- pass 1: row max (masking only in the ragged last block) ----
+      const bool full = valid >= 128;
+      float mx = full ? row_max_pass<false>(t_s, valid) : row_max_pass<true>(t_s, valid);
       mx *= sl2;
 
       // ---- lazy correction: rescale (l, O) only when the max grew by more than 2^8 ----
@@ -194,27 +259,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
 
       // ---- pass 2: P = exp2(S*scale - m) -> bf16 pairs into TMEM columns [0,64), running sum ----
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tc_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = c * 32 + 2 * i;
-          float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m));
-          float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m));
-          p0 = (col < valid) ? p0 : 0.f;
-          p1 = (col + 1 < valid) ? p1 : 0.f;
-          l0 += p0;
-          l1 += p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(t_s + c * 16, pk);  // trails the S columns already consumed: [16c,16c+16) <= 32c
-      }
-      l += l0 + l1;
+      l += full ? row_exp_pass<false>(t_s, sl2, m, valid) : row_exp_pass<true>(t_s, sl2, m, valid);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_full);

@@ -8,8 +8,9 @@
 //   warp 1      MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator;
 //                              two accumulator stages so tile i+1's mainloop overlaps tile i's epilogue
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       tcgen05.ld (thread == row) -> +bias -> activation -> bf16 ->
-//                              128B-swizzled smem staging -> TMA store (coalesced, clips the M tail)
+//   warps 4..11 epilogue       tcgen05.ld (thread == row; two warps share a TMEM lane quarter and split the
+//                              columns) -> +bias -> activation -> bf16/fp32 -> 128B-swizzled smem staging ->
+//                              TMA store (coalesced, clips the M tail)
 // A second epilogue (EPI_JIGSAW) fuses the regression head's last Linear with the score activation and
 // the jigsaw scatter (reference: model/cross_reference.py:45-50,82-87, model/regression_layer.py:26-62,
 // utils/misc/image.py:8-21): out[b, 14r+i, 14c+j] = act(z[b, r*pw+c, 14i+j]).
@@ -23,7 +24,8 @@ namespace xs {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 constexpr int ACC_STAGE_COLS = 256;  // TMEM column offset between the two accumulator stages
 constexpr int JIG_LD = 197;          // padded row length of the fp32 score staging tile
 
@@ -91,7 +93,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one elected lane per epilogue warp
+      mbar_init(&tmem_empty[s], 8);  // one elected lane per epilogue warp
     }
     fence_mbar_init();
   }
@@ -143,8 +145,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int epi_tid = threadIdx.x - 128;  // 0..127 == row of the tile
-    const int q = epi_tid >> 5;             // TMEM lane quarter this warp may access
+    const int epi_tid = threadIdx.x - 128;  // 0..255
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;       // which half of each column chunk this warp handles
+    const int row = q * 32 + lane;          // row of the tile owned by this thread
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t chunk_counter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -155,6 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       if constexpr (EPI == EPI_STORE) {
         constexpr int CW = (OUT == OUT_F32) ? 32 : 64;  // columns per 128-byte staging row
+        constexpr int HV = CW / 2;                       // accumulator values per thread per chunk
         constexpr int NCHUNK = BN / CW;
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
@@ -162,10 +167,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ++chunk_counter;
           // the TMA store that last read this staging buffer (two chunks ago) must have drained
           if (epi_tid == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          uint32_t v0[32], v1[32];
-          tmem_ld32(taddr0 + c * CW, v0);
-          if constexpr (OUT == OUT_BF16) tmem_ld32(taddr0 + c * CW + 32, v1);
+          named_bar_sync(1, EPI_THREADS);
+          uint32_t v[HV];
+          if constexpr (HV == 32) tmem_ld32(taddr0 + c * CW + half * HV, v);
+          else tmem_ld16(taddr0 + c * CW + half * HV, v);
           tc_wait_ld();
           if (c == NCHUNK - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
@@ -173,15 +178,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
           }
           const int n0 = n_blk * BN + c * CW;
-          uint8_t* srow = staging + buf * (GEMM_BM * 128) + epi_tid * 128;
-          const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+          uint8_t* srow = staging + buf * (GEMM_BM * 128) + row * 128;
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + half * HV);
           // 128B swizzle: 16-byte chunk index XOR (row mod 8); conflict-free for thread==row writes
           if constexpr (OUT == OUT_BF16) {
 #pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {
-              const float4 ba = __ldg(b4 + j8 * 2), bb = __ldg(b4 + j8 * 2 + 1);
-              const uint32_t* v = (j8 < 4) ? v0 : v1;
-              const int o = (j8 & 3) * 8;
+            for (int j = 0; j < 4; ++j) {
+              const float4 ba = __ldg(b4 + j * 2), bb = __ldg(b4 + j * 2 + 1);
+              const int o = j * 8;
               const float x0 = apply_act<ACT>(__uint_as_float(v[o + 0]) + ba.x);
               const float x1 = apply_act<ACT>(__uint_as_float(v[o + 1]) + ba.y);
               const float x2 = apply_act<ACT>(__uint_as_float(v[o + 2]) + ba.z);
@@ -195,22 +199,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               pk.y = pack_bf16x2(x2, x3);
               pk.z = pack_bf16x2(x4, x5);
               pk.w = pack_bf16x2(x6, x7);
-              *reinterpret_cast<uint4*>(srow + ((j8 ^ (epi_tid & 7)) << 4)) = pk;
+              *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = pk;
             }
           } else {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 ba = __ldg(b4 + j4);
+            for (int j = 0; j < 4; ++j) {
+              const float4 ba = __ldg(b4 + j);
               float4 o4;
-              o4.x = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 0]) + ba.x);
-              o4.y = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 1]) + ba.y);
-              o4.z = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 2]) + ba.z);
-              o4.w = apply_act<ACT>(__uint_as_float(v0[j4 * 4 + 3]) + ba.w);
-              *reinterpret_cast<float4*>(srow + ((j4 ^ (epi_tid & 7)) << 4)) = o4;
+              o4.x = apply_act<ACT>(__uint_as_float(v[j * 4 + 0]) + ba.x);
+              o4.y = apply_act<ACT>(__uint_as_float(v[j * 4 + 1]) + ba.y);
+              o4.z = apply_act<ACT>(__uint_as_float(v[j * 4 + 2]) + ba.z);
+              o4.w = apply_act<ACT>(__uint_as_float(v[j * 4 + 3]) + ba.w);
+              *reinterpret_cast<float4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = o4;
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, EPI_THREADS);
           if (epi_tid == 0) {
             tma_store_2d(&tmC, staging + buf * (GEMM_BM * 128), n0, m_blk * GEMM_BM);
             tma_store_commit();
@@ -220,12 +224,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---- regression head: activation + jigsaw scatter (fp32 score map) ----
         float* stile = reinterpret_cast<float*>(staging);
         constexpr int NCHUNK = BN / 32;
+        constexpr int LAST = ((NCHUNK - 1) & 1);  // parity of the last chunk
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
+        for (int c = half; c < NCHUNK; c += 2) {
           uint32_t v[32];
           tmem_ld32(taddr0 + c * 32, v);
           tc_wait_ld();
-          if (c == NCHUNK - 1) {
+          if (c + 2 >= NCHUNK) {  // this warp's last chunk
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
@@ -237,15 +242,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float z = __uint_as_float(v[j]) + __ldg(bias + k);
               float s = jp.use_tanh ? tanhf(z) : 1.0f / (1.0f + expf(-z));
               if (jp.power != 1.0f) s = powf(s, jp.power);
-              stile[epi_tid * JIG_LD + k] = s;
+              stile[row * JIG_LD + k] = s;
             }
           }
         }
-        named_bar_sync(1, 128);
+        (void)LAST;
+        named_bar_sync(1, EPI_THREADS);
         const int m0 = m_blk * GEMM_BM;
         const int rows_valid = min(GEMM_BM, M - m0);
         // (i, token, j) order: consecutive tokens of one grid row are contiguous in the image row
-        for (int e = epi_tid; e < 14 * GEMM_BM * 14; e += 128) {
+        for (int e = epi_tid; e < 14 * GEMM_BM * 14; e += EPI_THREADS) {
           const int i = e / (GEMM_BM * 14);
           const int rem = e - i * (GEMM_BM * 14);
           const int tt = rem / 14;
@@ -260,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 stile[tt * JIG_LD + i * 14 + j];
           }
         }
-        named_bar_sync(1, 128);  // staging tile is reused by the next tile
+        named_bar_sync(1, EPI_THREADS);  // staging tile is reused by the next tile
       }
       acc_stage ^= 1;
       if (acc_stage == 0) acc_phase ^= 1;

