@@ -5,14 +5,18 @@
 // (model/customised_transformer/transformer.py:182-205 -> $SP/torch/nn/functional.py:6630-6692, 8 heads x 48).
 //
 // One CTA = one (batch, head, 128-query tile, kv split); two CTAs are co-resident per SM so one CTA's
-// softmax overlaps the other's tensor-core work.  192 threads:
+// softmax overlaps the other's tensor-core work.  320 threads:
 //   warp 0      TMA producer: Q tile once, then K_j / V_j tiles [128 x 64] into a 2-stage ring
 //   warp 1      TMEM allocator + MMA issuer:  S = Q K_j^T  (SS, K-major operands, 128B swizzle)
-//                                             O += P_j V_j (TS: P read from TMEM, V MN-major from smem)
-//   warps 2..5  softmax: thread == query row (tcgen05.ld 32x32b), online max/sum in the log2 domain,
-//               lazy O rescale (only when the running max grows by > 8), P written back to TMEM as bf16
-//               over the S columns, final O / l and log-sum-exp.
-// TMEM: 256 columns: S/P [0,128), O [128, 128+DV).
+//                                             O_h += P_j[:, half h] V_j[half h]  (TS: P from TMEM, V MN-major smem)
+//   warps 2..9  softmax, two threads per query row: the 128 key columns of a block are split into two halves
+//               that run as independent online-softmax streams (own running max / sum and own O accumulator),
+//               so no per-block exchange is needed; the halves are merged once at the end with the split-KV
+//               identity.  This doubles the warps available to hide MUFU/TMEM latency (4 per scheduler with
+//               two CTAs) -- attention at head dim 64/48 is exp-bound (MUFU 16/clk/SM), not MMA-bound.
+//               Per block: tcgen05.ld (thread == row), max, lazy O rescale (only when the running max grows
+//               by > 2^8), P = exp2(S*scale - m) written back as bf16 over the thread's own S columns.
+// TMEM (256 columns): S [0,128) (P_0 aliases [0,32), P_1 aliases [64,96)), O_0 [128,128+DV), O_1 [192,192+DV).
 // Head dim 48 (decoder) uses 64-wide padded head slots in global memory: QK^T issues 3 K-steps (48) and
 // PV uses N=48, so no padded FLOPs are executed.
 // Rows / keys beyond the sequence are zero-filled by TMA (3-D tensor maps) and masked to -inf here.
@@ -22,9 +26,10 @@
 
 namespace xs {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr uint32_t ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: [128 rows][64 bf16], 128B swizzle
-constexpr uint32_t ATT_SMEM_BYTES = 5 * ATT_TILE_BYTES + 256 + 1024;
+constexpr uint32_t ATT_XCHG_BYTES = 2 * 128 * 8;   // (m, l) of both halves for the final merge
+constexpr uint32_t ATT_SMEM_BYTES = 5 * ATT_TILE_BYTES + ATT_XCHG_BYTES + 256 + 1024;
 
 struct AttnParams {
   void* o;
@@ -38,53 +43,49 @@ struct AttnParams {
   float scale_log2;
 };
 
-// ---- softmax building blocks (thread == query row; S row = 128 fp32 TMEM columns at t_s) -------------------
+// ---- softmax building blocks: one thread owns 64 fp32 S columns of its row, at TMEM address t_s ------------
 template <bool MASKED>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int col0, int valid) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+__device__ __forceinline__ float chunk_max16(const uint32_t (&v)[16], int col0, int valid) {
+  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
+  for (int i = 0; i < 16; i += 2) {
     if constexpr (MASKED) {
       m0 = fmaxf(m0, (col0 + i + 0 < valid) ? __uint_as_float(v[i + 0]) : -INFINITY);
       m1 = fmaxf(m1, (col0 + i + 1 < valid) ? __uint_as_float(v[i + 1]) : -INFINITY);
-      m2 = fmaxf(m2, (col0 + i + 2 < valid) ? __uint_as_float(v[i + 2]) : -INFINITY);
-      m3 = fmaxf(m3, (col0 + i + 3 < valid) ? __uint_as_float(v[i + 3]) : -INFINITY);
     } else {
       m0 = fmaxf(m0, __uint_as_float(v[i + 0]));
       m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-      m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-      m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
     }
   }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  return fmaxf(m0, m1);
 }
 
-// raw (unscaled) row max over the 128 columns; the TMEM load of chunk c+1 is in flight while chunk c is reduced
+// raw (unscaled) max over the 64 columns; the TMEM load of chunk c+1 is in flight while chunk c is reduced
 template <bool MASKED>
-__device__ __forceinline__ float row_max_pass(uint32_t t_s, int valid) {
-  uint32_t va[32], vb[32];
-  tmem_ld32(t_s, va);
-  tmem_ld_wait32(va);
-  tmem_ld32(t_s + 32, vb);
-  float mx = chunk_max<MASKED>(va, 0, valid);
-  tmem_ld_wait32(vb);
-  tmem_ld32(t_s + 64, va);
-  mx = fmaxf(mx, chunk_max<MASKED>(vb, 32, valid));
-  tmem_ld_wait32(va);
-  tmem_ld32(t_s + 96, vb);
-  mx = fmaxf(mx, chunk_max<MASKED>(va, 64, valid));
-  tmem_ld_wait32(vb);
-  return fmaxf(mx, chunk_max<MASKED>(vb, 96, valid));
+__device__ __forceinline__ float half_row_max(uint32_t t_s, int col_base, int valid) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(t_s, va);
+  tmem_ld_wait16(va);
+  tmem_ld16(t_s + 16, vb);
+  float mx = chunk_max16<MASKED>(va, col_base, valid);
+  tmem_ld_wait16(vb);
+  tmem_ld16(t_s + 32, va);
+  mx = fmaxf(mx, chunk_max16<MASKED>(vb, col_base + 16, valid));
+  tmem_ld_wait16(va);
+  tmem_ld16(t_s + 48, vb);
+  mx = fmaxf(mx, chunk_max16<MASKED>(va, col_base + 32, valid));
+  tmem_ld_wait16(vb);
+  return fmaxf(mx, chunk_max16<MASKED>(vb, col_base + 48, valid));
 }
 
-// P = exp2(S*sl2 - m) for 32 columns -> 16 packed bf16 pairs stored to TMEM at t_dst; returns the partial row sum
+// P = exp2(S*sl2 - m) for 16 columns -> 8 packed bf16 pairs stored to TMEM at t_dst; returns the partial sum
 template <bool MASKED>
-__device__ __forceinline__ float chunk_exp_store(const uint32_t (&v)[32], uint32_t t_dst, float sl2, float m, int col0,
-                                                 int valid) {
-  uint32_t pk[16];
+__device__ __forceinline__ float chunk_exp_store16(const uint32_t (&v)[16], uint32_t t_dst, float sl2, float m,
+                                                   int col0, int valid) {
+  uint32_t pk[8];
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < 8; ++i) {
     float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m));
     float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m));
     if constexpr (MASKED) {
@@ -95,26 +96,27 @@ __device__ __forceinline__ float chunk_exp_store(const uint32_t (&v)[32], uint32
     l1 += p1;
     pk[i] = pack_bf16x2(p0, p1);
   }
-  tmem_st16(t_dst, pk);
+  tmem_st8(t_dst, pk);
   return l0 + l1;
 }
 
-// second pass over the S row; P overwrites the S columns already consumed (P cols [16c,16c+16) <= S cols < 32c+32)
+// second pass; P (32 packed columns) overwrites the first half of the thread's own S columns, always behind
+// the columns already consumed: P cols [8c, 8c+8) <= S cols < 16c+16
 template <bool MASKED>
-__device__ __forceinline__ float row_exp_pass(uint32_t t_s, float sl2, float m, int valid) {
-  uint32_t va[32], vb[32];
-  tmem_ld32(t_s, va);
-  tmem_ld_wait32(va);
-  tmem_ld32(t_s + 32, vb);
-  float l = chunk_exp_store<MASKED>(va, t_s, sl2, m, 0, valid);
-  tmem_ld_wait32(vb);
-  tmem_ld32(t_s + 64, va);
-  l += chunk_exp_store<MASKED>(vb, t_s + 16, sl2, m, 32, valid);
-  tmem_ld_wait32(va);
-  tmem_ld32(t_s + 96, vb);
-  l += chunk_exp_store<MASKED>(va, t_s + 32, sl2, m, 64, valid);
-  tmem_ld_wait32(vb);
-  l += chunk_exp_store<MASKED>(vb, t_s + 48, sl2, m, 96, valid);
+__device__ __forceinline__ float half_row_exp(uint32_t t_s, float sl2, float m, int col_base, int valid) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(t_s, va);
+  tmem_ld_wait16(va);
+  tmem_ld16(t_s + 16, vb);
+  float l = chunk_exp_store16<MASKED>(va, t_s, sl2, m, col_base, valid);
+  tmem_ld_wait16(vb);
+  tmem_ld16(t_s + 32, va);
+  l += chunk_exp_store16<MASKED>(vb, t_s + 8, sl2, m, col_base + 16, valid);
+  tmem_ld_wait16(va);
+  tmem_ld16(t_s + 48, vb);
+  l += chunk_exp_store16<MASKED>(va, t_s + 16, sl2, m, col_base + 32, valid);
+  tmem_ld_wait16(vb);
+  l += chunk_exp_store16<MASKED>(vb, t_s + 24, sl2, m, col_base + 48, valid);
   return l;
 }
 
@@ -127,15 +129,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* smQ = smem;
   uint8_t* smK = smem + ATT_TILE_BYTES;      // 2 stages
   uint8_t* smV = smem + 3 * ATT_TILE_BYTES;  // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
+  float2* xchg = reinterpret_cast<float2*>(smem + 5 * ATT_TILE_BYTES);  // [2][128] (m, l)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES + ATT_XCHG_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* v_full = bars + 3;    // [2]
   uint64_t* kv_empty = bars + 5;  // [2]
   uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* p_full = bars + 8;    // [2]: one per column half
+  uint64_t* o_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,9 +161,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&kv_empty[s], 1);
+      mbar_init(&p_full[s], 128);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -169,8 +172,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // fp32 S, 128 columns; bf16 P aliases columns [0,64)
-  const uint32_t tmem_O = tmem_base + 128;  // fp32 O, DV columns
+  const uint32_t tmem_S = tmem_base;  // fp32 S, 128 columns
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -203,43 +205,62 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 idesc_qk, k != 0 ? 1u : 0u);
       }
       tc_commit(s_full);
-      // softmax has turned S_j into P_j (and rescaled O if the row max moved)
-      mbar_wait(p_full, j & 1);
       mbar_wait(&v_full[s], ph);
-      tc_fence_after();
       const uint32_t v_addr = smem_u32(smV + s * ATT_TILE_BYTES);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
-        umma_ts(tmem_O, tmem_S + k * 8, umma_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv,
-                (j | k) != 0 ? 1u : 0u);
+      for (int hf = 0; hf < 2; ++hf) {
+        // half hf of the softmax has turned its S columns into P (and rescaled O_hf if its max moved)
+        mbar_wait(&p_full[hf], j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
+          umma_ts(tmem_base + 128 + hf * 64, tmem_S + hf * 64 + k * 8,
+                  umma_desc_sw128(v_addr + (hf * 4 + k) * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
       }
       tc_commit(&kv_empty[s]);  // K_j and V_j are free once QK_j / PV_j have completed
     }
     tc_commit(o_full);
   } else if (warp >= 2) {
-    // ===================== softmax / correction / epilogue (thread == query row) =====================
-    const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+    // ===================== softmax / correction / epilogue =====================
+    const int q = warp & 3;           // TMEM lane quarter accessible to this warp
+    const int hf = (warp - 2) >> 2;   // column half handled by this thread
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t t_s = tmem_S + lane_off;
-    const uint32_t t_o = tmem_O + lane_off;
+    const uint32_t t_s = tmem_S + lane_off + hf * 64;
+    const uint32_t t_o = tmem_base + lane_off + 128 + hf * 64;
+    const int col_base = hf * 64;
     const float sl2 = p.scale_log2;
-    float m = -INFINITY;  // running (possibly stale) max, log2 domain
+    float m = -INFINITY;  // running (possibly stale) max of this half's stream, log2 domain
     float l = 0.f;        // running sum of exp2(s - m)
 
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int valid = kv_end - (kv_begin + j * 128);  // columns >= valid are past the sequence end
-
-      // ---- pass 1: row max (masking only in the ragged last block) ----
       const bool full = valid >= 128;
-      float mx = full ? row_max_pass<false>(t_s, valid) : row_max_pass<true>(t_s, valid);
+      if (!full && valid <= col_base) {
+        // this half of the ragged last block is entirely past the end: contributes nothing (P = 0)
+        uint32_t z[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st8(t_s + c * 8, z);
+        if (j == 0) {  // O_hf was never written: the PV below runs with accumulate = 0 over P = 0 -> zeros
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[hf]);
+        continue;
+      }
+
+      // ---- pass 1: max of this half (masking only in the ragged last block) ----
+      float mx = full ? half_row_max<false>(t_s, col_base, valid) : half_row_max<true>(t_s, col_base, valid);
       mx *= sl2;
 
-      // ---- lazy correction: rescale (l, O) only when the max grew by more than 2^8 ----
-      const bool need = mx > m + 8.0f;  // always true for j == 0 (m = -inf)
+      // ---- lazy correction: rescale (l, O_hf) only when the max grew by more than 2^8 ----
+      const bool need = mx > m + 8.0f;  // always true on the first block (m = -inf)
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = need ? mx : m;
         const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
@@ -249,7 +270,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int c = 0; c < DV / 16; ++c) {
             uint32_t v[16];
             tmem_ld16(t_o + c * 16, v);
-            tc_wait_ld();
+            tmem_ld_wait16(v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
             tmem_st16(t_o + c * 16, v);
@@ -258,52 +279,75 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         m = m_new;
       }
 
-      // ---- pass 2: P = exp2(S*scale - m) -> bf16 pairs into TMEM columns [0,64), running sum ----
-      l += full ? row_exp_pass<false>(t_s, sl2, m, valid) : row_exp_pass<true>(t_s, sl2, m, valid);
+      // ---- pass 2: P = exp2(S*scale - m) -> bf16 pairs over this thread's own S columns ----
+      l += full ? half_row_exp<false>(t_s, sl2, m, col_base, valid) : half_row_exp<true>(t_s, sl2, m, col_base, valid);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[hf]);
     }
 
-    // ---- epilogue: O / l, log-sum-exp ----
+    // ---- merge the two halves (split-KV identity) and write O / l, log-sum-exp ----
+    xchg[hf * 128 + row] = make_float2(m, l);
+    named_bar_sync(1, 256);
+    const float2 other = xchg[(hf ^ 1) * 128 + row];
+    const float m_all = fmaxf(m, other.x);  // at least one half saw a valid column, so m_all is finite
+    const float w_me = fast_exp2(m - m_all), w_ot = fast_exp2(other.x - m_all);
+    const float l_all = l * w_me + other.y * w_ot;
+    const float inv = 1.0f / l_all;
+    const float w0 = (hf == 0 ? w_me : w_ot) * inv;  // weight of O_0
+    const float w1 = (hf == 0 ? w_ot : w_me) * inv;  // weight of O_1
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv = 1.0f / l;
     const int row_g = q0 + row;
     const bool row_ok = row_g < p.Lq;
+    // this thread writes output columns [hf*DV/2, (hf+1)*DV/2)
+    constexpr int HC = DV / 2;  // 32 or 24
+    const uint32_t t_o0 = tmem_base + lane_off + 128 + hf * HC;
+    const uint32_t t_o1 = tmem_base + lane_off + 192 + hf * HC;
     const long long o_off = static_cast<long long>(split) * p.o_split_stride +
                             static_cast<long long>(b) * p.o_batch_stride +
-                            static_cast<long long>(row_g) * p.o_row_stride + static_cast<long long>(h) * DV;
+                            static_cast<long long>(row_g) * p.o_row_stride + static_cast<long long>(h) * DV + hf * HC;
 #pragma unroll
-    for (int c = 0; c < DV / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld16(t_o + c * 16, v);
-      tc_wait_ld();
+    for (int c = 0; c < HC / 8; ++c) {
+      uint32_t a8[8], b8[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(a8[0]), "=r"(a8[1]), "=r"(a8[2]), "=r"(a8[3]), "=r"(a8[4]), "=r"(a8[5]), "=r"(a8[6]),
+                     "=r"(a8[7])
+                   : "r"(t_o0 + c * 8)
+                   : "memory");
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(b8[0]), "=r"(b8[1]), "=r"(b8[2]), "=r"(b8[3]), "=r"(b8[4]), "=r"(b8[5]), "=r"(b8[6]),
+                     "=r"(b8[7])
+                   : "r"(t_o1 + c * 8)
+                   : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;"
+                   : "+r"(a8[0]), "+r"(a8[1]), "+r"(a8[2]), "+r"(a8[3]), "+r"(a8[4]), "+r"(a8[5]), "+r"(a8[6]),
+                     "+r"(a8[7]), "+r"(b8[0]), "+r"(b8[1]), "+r"(b8[2]), "+r"(b8[3]), "+r"(b8[4]), "+r"(b8[5]),
+                     "+r"(b8[6]), "+r"(b8[7])
+                   :
+                   : "memory");
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = __uint_as_float(a8[i]) * w0 + __uint_as_float(b8[i]) * w1;
       if (row_ok) {
         if (p.o_is_f32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.o) + o_off + c * 16);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]) * inv, __uint_as_float(v[4 * i + 1]) * inv,
-                                 __uint_as_float(v[4 * i + 2]) * inv, __uint_as_float(v[4 * i + 3]) * inv);
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.o) + o_off + c * 8);
+          dst[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+          dst[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
         } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.o) + o_off + c * 16);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
-            pk.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
-            pk.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
-            pk.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
-            dst[i] = pk;
-          }
+          uint4 pk;
+          pk.x = pack_bf16x2(o8[0], o8[1]);
+          pk.y = pack_bf16x2(o8[2], o8[3]);
+          pk.z = pack_bf16x2(o8[4], o8[5]);
+          pk.w = pack_bf16x2(o8[6], o8[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.o) + o_off + c * 8) = pk;
         }
       }
     }
-    if (p.lse != nullptr && row_ok) {
+    if (p.lse != nullptr && row_ok && hf == 0) {
       // natural-log LSE of the scaled logits: ln sum_j exp(s_j * scale)
       p.lse[static_cast<long long>(split) * p.lse_split_stride +
-            (static_cast<long long>(b) * p.heads + h) * p.Lq + row_g] = (m + log2f(l)) * 0.6931471805599453f;
+            (static_cast<long long>(b) * p.heads + h) * p.Lq + row_g] = (m_all + log2f(l_all)) * 0.6931471805599453f;
     }
   }
 

@@ -133,18 +133,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on the phase bit.  A pipeline bug would otherwise hang the GPU box until the job limit, so
-// the wait traps after ~4e9 cycles (seconds) and the host sees a launch failure instead.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Spin on the phase bit.  try_wait parks the warp in hardware for up to the suspend-time hint, so the loop
+// issues few instructions.  A pipeline bug would otherwise hang the GPU box until the job limit, so the wait
+// traps after a few seconds (clock checked every 4096 polls) and the host sees a launch failure instead.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+  for (;;) {
+    for (int i = 0; i < 4096; ++i)
+      if (mbar_try_wait_hint(bar, parity)) return;
+    if (clock64() - t0 > 8000000000LL) {
       printf("xs: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i)
+    if (mbar_try_wait_hint(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -300,6 +322,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15])
+               :
+               : "memory");
 }
 // tcgen05.wait::ld that also names the destination registers, so the compiler cannot move their consumers
 // above the wait (the loads are asynchronous until this point)
