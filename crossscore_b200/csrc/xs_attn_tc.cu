@@ -5,7 +5,7 @@
 // (model/customised_transformer/transformer.py:182-205 -> $SP/torch/nn/functional.py:6630-6692, 8 heads x 48).
 //
 // One CTA = one (batch, head, 128-query tile, kv split); two CTAs are co-resident per SM.  192 threads:
-//   warp 0      TMA producer: Q tile once, then K_j / V_j tiles [64 keys x 64] into two 4-stage rings
+//   warp 0      TMA producer: Q tile once, then K_j / V_j tiles [64 keys x 64] into a 4-stage ring
 //   warp 1      TMEM allocator + MMA issuer:  S_b = Q K_j^T  (SS, K-major operands, 128B swizzle, N = 64)
 //                                             O  += P_j V_j  (TS: P read from TMEM, V MN-major from smem)
 //   warps 2..5  softmax: thread == query row (tcgen05.ld 32x32b), one pass over the 64 columns held in
@@ -59,14 +59,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* smV = smK + ATT_ST * ATT_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smV + ATT_ST * ATT_KV_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;                 // [ATT_ST]
-  uint64_t* k_empty = k_full + ATT_ST;         // [ATT_ST]
-  uint64_t* v_full = k_empty + ATT_ST;         // [ATT_ST]
-  uint64_t* v_empty = v_full + ATT_ST;         // [ATT_ST]
-  uint64_t* s_full = v_empty + ATT_ST;         // [2]
+  uint64_t* kv_full = bars + 1;                // [ATT_ST] K_j and V_j landed
+  uint64_t* kv_empty = kv_full + ATT_ST;       // [ATT_ST] PV_j complete: slot free (also read by the O rescale)
+  uint64_t* s_full = kv_empty + ATT_ST;        // [2]
   uint64_t* p_full = s_full + 2;               // [2]
-  uint64_t* pv_done = p_full + 2;              // completes once per PV_j
-  uint64_t* o_full = pv_done + 1;              // all PV complete
+  uint64_t* o_full = p_full + 2;               // all PV complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -87,16 +84,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_ST; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
     }
-    mbar_init(pv_done, 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -107,39 +101,44 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 128;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
-    mbar_expect_tx(q_full, ATT_Q_BYTES);
-    tma_load_3d(smQ, &tmQ, q_full, h * 64, q0, b);
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    if (elect_one_sync()) {
+      mbar_expect_tx(q_full, ATT_Q_BYTES);
+      tma_load_3d(smQ, &tmQ, q_full, h * 64, q0, b);
+    }
+    __syncwarp();
     for (int j = 0; j < nkv; ++j) {
       const int s = j % ATT_ST;
-      const uint32_t ph = (j / ATT_ST) & 1;
       const int kv0 = kv_begin + j * ATT_BKV;
-      mbar_wait(&k_empty[s], ph ^ 1);
-      mbar_expect_tx(&k_full[s], ATT_KV_BYTES);
-      tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, &k_full[s], h * 64, kv0, b_kv);
-      mbar_wait(&v_empty[s], ph ^ 1);
-      mbar_expect_tx(&v_full[s], ATT_KV_BYTES);
-      tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, &v_full[s], h * 64, kv0, b_kv);
+      mbar_wait(&kv_empty[s], ((j / ATT_ST) & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&kv_full[s], 2 * ATT_KV_BYTES);
+        tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, &kv_full[s], h * 64, kv0, b_kv);
+        tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, &kv_full[s], h * 64, kv0, b_kv);
+      }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BKV, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major ([kv][d], d contiguous)
-    const uint32_t q_addr = smem_u32(smQ);
+    const uint32_t tb = warp_uniform(tmem_base);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(smQ), 16);
+    const uint32_t k_lo0 = umma_desc_lo(smem_u32(smK), 16);
+    const uint32_t v_lo0 = umma_desc_lo(smem_u32(smV), 1024);
     auto issue_qk = [&](int jj) {
       const int s = jj % ATT_ST;
-      mbar_wait(&k_full[s], (jj / ATT_ST) & 1);
+      mbar_wait(&kv_full[s], (jj / ATT_ST) & 1);  // K_jj (and V_jj) have landed
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(smK + s * ATT_KV_BYTES);
-      const uint32_t d_s = tmem_base + (jj & 1) * 64;
+      if (elect_one_sync()) {
+        const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
+        const uint32_t d_s = tb + (jj & 1) * 64;
 #pragma unroll
-      for (int k = 0; k < DQK_STEPS; ++k) {
-        umma_ss(d_s, umma_desc_sw128(q_addr + k * 32, 16, 1024), umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc_qk,
-                k != 0 ? 1u : 0u);
+        for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        tc_commit(&s_full[jj & 1]);
       }
-      tc_commit(&k_empty[s]);
-      tc_commit(&s_full[jj & 1]);
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     issue_qk(0);
@@ -148,20 +147,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int s = j % ATT_ST;
       // softmax has turned S_{j&1} into P_j (and rescaled O if the row max moved)
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-      mbar_wait(&v_full[s], (j / ATT_ST) & 1);
       tc_fence_after();
-      const uint32_t v_addr = smem_u32(smV + s * ATT_KV_BYTES);
-      const uint32_t a_p = tmem_base + (j & 1) * 64;
+      if (elect_one_sync()) {
+        const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
+        const uint32_t a_p = tb + (j & 1) * 64;
 #pragma unroll
-      for (int k = 0; k < ATT_BKV / 16; ++k) {
-        // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
-        umma_ts(tmem_O, a_p + k * 8, umma_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < ATT_BKV / 16; ++k) {
+          // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
+          umma_ts_lh(tb + 128, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&kv_empty[s]);  // K_j / V_j slot free; also the "PV_j complete" signal for the O rescale
       }
-      tc_commit(&v_empty[s]);
-      tc_commit(pv_done);
+      __syncwarp();
       if (j + 2 < nkv) issue_qk(j + 2);  // overwrites S_{j&1} behind PV_j (tensor pipe executes in order)
     }
-    tc_commit(o_full);
+    if (elect_one_sync()) tc_commit(o_full);
+    __syncwarp();
   } else if (warp >= 2) {
     // ===================== softmax / correction / epilogue (thread == query row) =====================
     const int q = warp & 3;  // TMEM lane quarter accessible to this warp
@@ -211,8 +212,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
         l *= alpha;
         if (j > 0) {
-          // O must hold PV_0..PV_{j-1}: s_full(j) already implies PV_{j-2}; wait for PV_{j-1}
-          mbar_wait(pv_done, (j - 1) & 1);
+          // O must hold PV_0..PV_{j-1}: s_full(j) already implies PV_{j-2}; wait for PV_{j-1} (its slot's
+          // kv_empty phase; at most one phase behind, so the parity test cannot alias)
+          mbar_wait(&kv_empty[(j - 1) % ATT_ST], ((j - 1) / ATT_ST) & 1);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < DV / 16; ++c) {

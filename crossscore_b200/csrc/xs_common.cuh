@@ -248,6 +248,30 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// Split form used by the MMA-issuing warps: the high word is a constant, the low word is (addr >> 4) | LBO and
+// is advanced by plain 32-bit adds (K-step inside a 128B-swizzled row: +32 B -> +2; 16 MN-major rows: +2048 B -> +128).
+constexpr uint32_t UMMA_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+
+// One lane of a converged warp (elect.sync).  The MMA / TMA issuing warps stay converged and keep their
+// operands warp-uniform, so the tcgen05 / TMA instructions take uniform-register operands directly; a
+// `lane == 0` branch instead makes the compiler wrap every such instruction in an elect/R2UR waterfall loop
+// (~80 cycles per MMA, measured) that starves the tensor pipe when the MMAs are small.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Instruction descriptor, kind::f16 with bf16 A/B and fp32 accumulate.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                                 // D format f32
@@ -288,6 +312,50 @@ __device__ __forceinline__ void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// lo/hi descriptor forms (see umma_desc_lo)
+template <bool TF32>
+__device__ __forceinline__ void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %5};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %5};\n"
+        "mov.b64 db, {%2, %5};\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {

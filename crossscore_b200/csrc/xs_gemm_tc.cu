@@ -103,43 +103,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
-        tma_load_2d(smA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BKE, m_blk * GEMM_BM);
-        tma_load_2d(smB + stage * L::B_BYTES, &tmW, &full_bar[stage], kb * BKE, n_blk * BN);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
+          tma_load_2d(smA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BKE, m_blk * GEMM_BM);
+          tma_load_2d(smB + stage * L::B_BYTES, &tmW, &full_bar[stage], kb * BKE, n_blk * BN);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
     constexpr uint32_t idesc = (IN == IN_TF32) ? umma_idesc_tf32(GEMM_BM, BN) : umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+    const uint32_t tb = warp_uniform(tmem_base);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA), 16);
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB), 16);
     uint32_t stage = 0, phase = 0, acc_stage = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc_stage * ACC_STAGE_COLS;
+      const uint32_t d_tmem = tb + acc_stage * ACC_STAGE_COLS;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smA + stage * L::A_BYTES);
-        const uint32_t b_addr = smem_u32(smB + stage * L::B_BYTES);
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + stage * (L::A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (L::B_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row (16 bf16 or 8 tf32 each)
-          const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          if constexpr (IN == IN_TF32) umma_ss_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row (16 bf16 or 8 tf32 each)
+            umma_ss_lh<IN == IN_TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (kb == num_k - 1) tc_commit(&tmem_full[acc_stage]);  // accumulator complete -> epilogue
         }
-        tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&tmem_full[acc_stage]);  // accumulator complete -> epilogue
       acc_stage ^= 1;
       if (acc_stage == 0) acc_phase ^= 1;
     }
