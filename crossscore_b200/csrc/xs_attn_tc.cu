@@ -11,12 +11,13 @@
 //   warps 2..5  softmax: thread == query row (tcgen05.ld 32x32b), one pass over the 64 columns held in
 //               registers: max, lazy O rescale (only when the running max grows by > 2^8), P = exp2(S*scale - m)
 //               written back to TMEM as bf16 over the S columns, final O / l and log-sum-exp.
-// S is DOUBLE-BUFFERED in TMEM (S_0, S_1): QK_{j+2} is issued right behind PV_j, so S_{j+1} is already
-// complete when the softmax finishes block j and the MMA->softmax->MMA handshake latency (measured ~2.5k
-// cycles per round trip, more than the 512 MMA cycles of a block) is off the critical path; the softmax
+// S is TRIPLE-BUFFERED in TMEM (S_0..S_2): QK_{j+3} is issued right behind PV_j, so S_{j+1} is already
+// complete when the softmax finishes block j and the MMA->softmax->MMA handshake latency (measured ~2k
+// cycles per round trip, several times the MMA cycles of a block) is off the critical path; the softmax
 // warps stream continuously and the kernel runs at the exp (MUFU, 16/clk/SM) bound rather than on latency.
-// TMEM (256 columns, two CTAs per SM): S_0 [0,64), S_1 [64,128) (P_b aliases the first 32 columns of S_b),
-// O [128, 128+DV).
+// Barrier traffic is per warp: lane 0 polls / arrives, __syncwarp broadcasts.
+// TMEM (256 columns, two CTAs per SM): S_b [64b, 64b+64), b = 0..2 (P_b aliases the first 32 columns of S_b),
+// O [192, 192+DV).
 // Head dim 48 (decoder) uses 64-wide padded head slots in global memory: QK^T issues 3 K-steps (48) and
 // PV uses N=48, so no padded FLOPs are executed.
 // Rows / keys beyond the sequence are zero-filled by TMA (3-D tensor maps) and masked to -inf here.
@@ -31,6 +32,7 @@ namespace xs {
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_BKV = 64;                             // keys per block
 constexpr int ATT_ST = 4;                               // K and V ring depth
+constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK runs ATT_NS blocks ahead of PV)
 constexpr uint32_t ATT_Q_BYTES = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16], 128B swizzle
 constexpr uint32_t ATT_KV_BYTES = ATT_BKV * 64 * 2;     // 8 KB:  [64 keys][64 bf16]
 constexpr uint32_t ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_ST * ATT_KV_BYTES + 256 + 1024;
@@ -61,9 +63,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;                // [ATT_ST] K_j and V_j landed
   uint64_t* kv_empty = kv_full + ATT_ST;       // [ATT_ST] PV_j complete: slot free (also read by the O rescale)
-  uint64_t* s_full = kv_empty + ATT_ST;        // [2]
-  uint64_t* p_full = s_full + 2;               // [2]
-  uint64_t* o_full = p_full + 2;               // all PV complete
+  uint64_t* s_full = kv_empty + ATT_ST;        // [ATT_NS]
+  uint64_t* p_full = s_full + ATT_NS;          // [ATT_NS]
+  uint64_t* o_full = p_full + ATT_NS;          // all PV complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -87,9 +89,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ATT_NS; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&p_full[s], 4);  // one arrival per softmax warp
     }
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -99,7 +101,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + ATT_NS * 64;
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
@@ -133,33 +135,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
-        const uint32_t d_s = tb + (jj & 1) * 64;
+        const uint32_t d_s = tb + (jj % ATT_NS) * 64;
 #pragma unroll
         for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[jj & 1]);
+        tc_commit(&s_full[jj % ATT_NS]);
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (nkv > 1) issue_qk(1);
+    for (int jj = 0; jj < ATT_NS && jj < nkv; ++jj) issue_qk(jj);
     for (int j = 0; j < nkv; ++j) {
       const int s = j % ATT_ST;
-      // softmax has turned S_{j&1} into P_j (and rescaled O if the row max moved)
-      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      const int sb = j % ATT_NS;
+      // softmax has turned S_sb into P_j (and rescaled O if the row max moved)
+      mbar_wait(&p_full[sb], (j / ATT_NS) & 1);
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
-        const uint32_t a_p = tb + (j & 1) * 64;
+        const uint32_t a_p = tb + sb * 64;
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k) {
           // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
-          umma_ts_lh(tb + 128, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_ts_lh(tb + ATT_NS * 64, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         tc_commit(&kv_empty[s]);  // K_j / V_j slot free; also the "PV_j complete" signal for the O rescale
       }
       __syncwarp();
-      if (j + 2 < nkv) issue_qk(j + 2);  // overwrites S_{j&1} behind PV_j (tensor pipe executes in order)
+      if (j + ATT_NS < nkv) issue_qk(j + ATT_NS);  // overwrites S_sb behind PV_j (tensor pipe executes in order)
     }
     if (elect_one_sync()) tc_commit(o_full);
     __syncwarp();
@@ -174,12 +176,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     float l = 0.f;        // running sum of exp2(s - m)
 
     for (int j = 0; j < nkv; ++j) {
-      const uint32_t t_s = tmem_base + lane_off + (j & 1) * 64;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      const int sb = j % ATT_NS;
+      const uint32_t t_s = tmem_base + lane_off + sb * 64;
+      if (lane == 0) mbar_wait(&s_full[sb], (j / ATT_NS) & 1);
+      __syncwarp();
       tc_fence_after();
       if (p.dbg & 4) {  // timing experiment: no softmax work at all
         tc_fence_before();
-        mbar_arrive(&p_full[j & 1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sb]);
         continue;
       }
       uint32_t v0[32], v1[32];
@@ -212,9 +217,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
         l *= alpha;
         if (j > 0) {
-          // O must hold PV_0..PV_{j-1}: s_full(j) already implies PV_{j-2}; wait for PV_{j-1} (its slot's
-          // kv_empty phase; at most one phase behind, so the parity test cannot alias)
-          mbar_wait(&kv_empty[(j - 1) % ATT_ST], ((j - 1) / ATT_ST) & 1);
+          // O must hold PV_0..PV_{j-1}: wait for PV_{j-1} through its K/V slot's kv_empty phase (that slot is
+          // refilled only ATT_ST blocks later, so the parity test cannot alias)
+          if (lane == 0) mbar_wait(&kv_empty[(j - 1) % ATT_ST], ((j - 1) / ATT_ST) & 1);
+          __syncwarp();
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < DV / 16; ++c) {
@@ -259,11 +265,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_st16(t_s + 16, pk1);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[sb]);
     }
 
     // ---- epilogue: O / l, log-sum-exp ----
-    mbar_wait(o_full, 0);
+    if (lane == 0) mbar_wait(o_full, 0);
+    __syncwarp();
     tc_fence_after();
     const float inv = 1.0f / l;
     const int row_g = q0 + row;
