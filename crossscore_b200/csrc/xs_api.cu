@@ -97,7 +97,8 @@ int rows_final_ln_pe(const float*, const void*, const float*, const float*, floa
 int rows_im2col14(const float*, void*, int, int, int, int, int, cudaStream_t);
 int table_bilinear_ac(const float*, float*, int, int, int, int, int, cudaStream_t);
 int table_bicubic(const float*, float*, int, int, int, int, int, cudaStream_t);
-int rows_lse_merge(const float*, const float*, void*, float*, int, int, int, int, int, int, cudaStream_t);
+int rows_lse_merge(const float*, const float*, void*, float*, int, int, int, int, int, long long, long long, int,
+                   cudaStream_t);
 int rows_attn_probs(const void*, const void*, const float*, float*, int, int, int, int, int, int, int, long long,
                     long long, long long, long long, float, int, cudaStream_t);
 
@@ -214,9 +215,10 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
 }
 
 int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float* lse_out, int n_parts, int B, int Lq,
-                 int heads, int head_dim, int dtype, xs_stream_t stream) {
-  return rows_lse_merge(o_parts, lse_parts, out, lse_out, n_parts, B, Lq, heads, head_dim, dtype,
-                        static_cast<cudaStream_t>(stream));
+                 int heads, int head_dim, long long o_part_stride, long long lse_part_stride, int dtype,
+                 xs_stream_t stream) {
+  return rows_lse_merge(o_parts, lse_parts, out, lse_out, n_parts, B, Lq, heads, head_dim, o_part_stride,
+                        lse_part_stride, dtype, static_cast<cudaStream_t>(stream));
 }
 
 int xs_head_score_jigsaw(const void* A, int lda, const void* W, int ldw, const float* bias, float* score, int B,

@@ -33,6 +33,7 @@ constexpr int ATT_THREADS = 192;
 constexpr int ATT_BKV = 64;                             // keys per block
 constexpr int ATT_ST = 4;                               // K and V ring depth
 constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK runs ATT_NS blocks ahead of PV)
+constexpr float ATT_GROW = 16.0f;                       // log2 headroom of P above the stale row max before a rescale
 constexpr uint32_t ATT_Q_BYTES = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16], 128B swizzle
 constexpr uint32_t ATT_KV_BYTES = ATT_BKV * 64 * 2;     // 8 KB:  [64 keys][64 bf16]
 constexpr uint32_t ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_ST * ATT_KV_BYTES + 256 + 1024;
@@ -47,10 +48,40 @@ struct AttnParams {
   long long o_row_stride, o_batch_stride, o_split_stride;  // elements
   long long lse_split_stride;
   float scale_log2;
-  int dbg;  // timing experiments only (XS_ATTN_DBG): 2 skip exp, 4 skip the whole softmax
+  int dbg;  // timing experiments only (XS_ATTN_DBG): 4 skip the whole softmax
+  unsigned long long* prof;  // XS_ATTN_PROF=1 (PROF instantiation only): per-phase clock totals, see flash_attn_bf16_tc
 };
 
-template <int DQK_STEPS, int DV>
+// development-only phase timer: lane 0 of every softmax warp / the MMA warp accumulates clock deltas
+template <bool PROF>
+struct PhaseClock {
+  long long t;
+  unsigned long long acc[8];
+  __device__ __forceinline__ void start() {
+    if constexpr (PROF) {
+      t = clock64();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0;
+    }
+  }
+  __device__ __forceinline__ void lap(int i) {
+    if constexpr (PROF) {
+      const long long n = clock64();
+      acc[i] += static_cast<unsigned long long>(n - t);
+      t = n;
+    }
+  }
+  __device__ __forceinline__ void flush(unsigned long long* out, int base, int lane) {
+    if constexpr (PROF) {
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(out + base + i, acc[i]);
+      }
+    }
+  }
+};
+
+template <int DQK_STEPS, int DV, bool PROF>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -142,13 +173,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       __syncwarp();
     };
+    PhaseClock<PROF> pc;
+    pc.start();
     mbar_wait(q_full, 0);
     for (int jj = 0; jj < ATT_NS && jj < nkv; ++jj) issue_qk(jj);
+    pc.lap(0);  // prologue: Q + first S blocks issued
     for (int j = 0; j < nkv; ++j) {
       const int s = j % ATT_ST;
       const int sb = j % ATT_NS;
       // softmax has turned S_sb into P_j (and rescaled O if the row max moved)
       mbar_wait(&p_full[sb], (j / ATT_NS) & 1);
+      pc.lap(1);  // waiting for P_j
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
@@ -161,10 +196,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_commit(&kv_empty[s]);  // K_j / V_j slot free; also the "PV_j complete" signal for the O rescale
       }
       __syncwarp();
+      pc.lap(2);  // PV_j issue
       if (j + ATT_NS < nkv) issue_qk(j + ATT_NS);  // overwrites S_sb behind PV_j (tensor pipe executes in order)
+      pc.lap(3);  // K wait + QK_{j+NS} issue
     }
     if (elect_one_sync()) tc_commit(o_full);
     __syncwarp();
+    pc.flush(p.prof, 8, lane);
   } else if (warp >= 2) {
     // ===================== softmax / correction / epilogue (thread == query row) =====================
     const int q = warp & 3;  // TMEM lane quarter accessible to this warp
@@ -174,12 +212,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float sl2 = p.scale_log2;
     float m = -INFINITY;  // running (possibly stale) max, log2 domain
     float l = 0.f;        // running sum of exp2(s - m)
+    PhaseClock<PROF> pc;
+    pc.start();
 
     for (int j = 0; j < nkv; ++j) {
       const int sb = j % ATT_NS;
       const uint32_t t_s = tmem_base + lane_off + sb * 64;
       if (lane == 0) mbar_wait(&s_full[sb], (j / ATT_NS) & 1);
       __syncwarp();
+      pc.lap(0);  // waiting for S_j
       tc_fence_after();
       if (p.dbg & 4) {  // timing experiment: no softmax work at all
         tc_fence_before();
@@ -192,6 +233,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_ld32(t_s + 32, v1);
       tmem_ld_wait32(v0);
       tmem_ld_wait32(v1);
+      pc.lap(1);  // tcgen05.ld of the S block
       const int valid = kv_end - (kv_begin + j * ATT_BKV);  // columns >= valid are past the sequence end
       if (valid < ATT_BKV) {
 #pragma unroll
@@ -200,19 +242,50 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (32 + i >= valid) v1[i] = 0xff800000u;
         }
       }
+      // ---- fused pass: P = exp2(S*scale - m) with the STALE running max m, while the max of THIS block is
+      // reduced on the ALU pipe in the shadow of the MUFU-bound exponentials.  (A separate max pass in front
+      // of the exponentials serialises two phases per warp, and the two co-resident CTAs' softmax warps fall
+      // into lock-step on the shared MUFU: measured 1083 clk per 128x64 block per SM vs the 512 clk MUFU
+      // bound.)  Exactness does not depend on m: any m gives the same softmax as long as 2^(s-m) stays in
+      // range (bf16 P and the fp32 sums keep their relative precision at any magnitude), so P is only recomputed
+      // when some row's block max exceeds m by more than ATT_GROW, which bounds P by 2^ATT_GROW and l by
+      // Lk * 2^ATT_GROW; the first block (m = -inf) always takes that path.
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      uint32_t pk0[16], pk1[16];
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (j > 0) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v0[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(v1[i]));
-        mx3 = fmaxf(mx3, __uint_as_float(v1[i + 1]));
+        for (int i = 0; i < 16; ++i) {
+          const float s0 = __uint_as_float(v0[2 * i]), s1 = __uint_as_float(v0[2 * i + 1]);
+          const float s2 = __uint_as_float(v1[2 * i]), s3 = __uint_as_float(v1[2 * i + 1]);
+          const float a0 = fast_exp2(fmaf(s0, sl2, -m));
+          const float a1 = fast_exp2(fmaf(s1, sl2, -m));
+          const float b0 = fast_exp2(fmaf(s2, sl2, -m));
+          const float b1 = fast_exp2(fmaf(s3, sl2, -m));
+          mx0 = fmaxf(mx0, s0);
+          mx1 = fmaxf(mx1, s1);
+          mx2 = fmaxf(mx2, s2);
+          mx3 = fmaxf(mx3, s3);
+          l0 += a0;
+          l1 += a1;
+          l2 += b0;
+          l3 += b1;
+          pk0[i] = pack_bf16x2(a0, a1);
+          pk1[i] = pack_bf16x2(b0, b1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(v0[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(v1[i]));
+          mx3 = fmaxf(mx3, __uint_as_float(v1[i + 1]));
+        }
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
-
-      // ---- lazy correction: rescale (l, O) only when the max grew by more than 2^8 ----
-      const bool need = mx > m + 8.0f;  // always true on the first block (m = -inf)
+      const bool need = mx > m + ATT_GROW;  // always true on the first block (m = -inf)
       if (__any_sync(0xffffffffu, need)) {
+        // ---- slow path: move this row's reference max, rescale (l, O), recompute P for the block ----
         const float m_new = need ? mx : m;
         const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
         l *= alpha;
@@ -233,12 +306,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         m = m_new;
-      }
-
-      // ---- P = exp2(S*scale - m) -> bf16 pairs into the first 32 columns of this S buffer ----
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      uint32_t pk0[16], pk1[16];
-      if (!(p.dbg & 2)) {
+        l0 = l1 = l2 = l3 = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, -m));
@@ -252,26 +320,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           pk0[i] = pack_bf16x2(a0, a1);
           pk1[i] = pack_bf16x2(b0, b1);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pk0[i] = pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-          pk1[i] = pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-        }
-        l0 = 1.f;
       }
       l += (l0 + l1) + (l2 + l3);
+      pc.lap(2);  // max / exp2 / pack (incl. the rare rescale path)
       tmem_st16(t_s, pk0);
       tmem_st16(t_s + 16, pk1);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
+      pc.lap(3);  // tcgen05.st of P + fences + arrive
     }
 
     // ---- epilogue: O / l, log-sum-exp ----
     if (lane == 0) mbar_wait(o_full, 0);
     __syncwarp();
+    pc.lap(4);  // waiting for the last PV
     tc_fence_after();
     const float inv = 1.0f / l;
     const int row_g = q0 + row;
@@ -310,6 +374,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       p.lse[static_cast<long long>(split) * p.lse_split_stride +
             (static_cast<long long>(b) * p.heads + h) * p.Lq + row_g] = (m + log2f(l)) * 0.6931471805599453f;
     }
+    pc.lap(5);  // epilogue stores
+    pc.flush(p.prof, 0, lane);
   }
 
   tc_fence_before();
@@ -318,6 +384,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+// Development aid (XS_ATTN_PROF=1): run the instrumented instantiation synchronously and print the average
+// clocks each softmax warp / MMA warp spent per phase (per CTA lifetime) to stderr.
+static int launch_attn_prof(int head_dim, dim3 grid, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                            const CUtensorMap& tmV, AttnParams p, cudaStream_t stream) {
+  static unsigned long long* buf = nullptr;
+  if (buf == nullptr) XS_CUDA(cudaMalloc(&buf, 16 * sizeof(unsigned long long)));
+  XS_CUDA(cudaMemsetAsync(buf, 0, 16 * sizeof(unsigned long long), stream));
+  p.prof = buf;
+  if (head_dim == 64) {
+    auto kern = attn_tc_kernel<4, 64, true>;
+    XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+    kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    auto kern = attn_tc_kernel<3, 48, true>;
+    XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+    kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  }
+  XS_LAUNCH_CHECK();
+  XS_CUDA(cudaStreamSynchronize(stream));
+  unsigned long long h[16];
+  XS_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
+  const double ctas = double(grid.x) * grid.y * grid.z;
+  const int nkv = (p.split_len < p.Lk ? p.split_len : p.Lk + ATT_BKV - 1) / ATT_BKV;
+  fprintf(stderr, "attn prof (clk per CTA, ~%d kv blocks): softmax warp: wait_S %.0f  ld_S %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
+                  "epi %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
+          nkv, h[0] / ctas / 4, h[1] / ctas / 4, h[2] / ctas / 4, h[3] / ctas / 4, h[4] / ctas / 4, h[5] / ctas / 4,
+          h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
+  return 0;
 }
 
 // q/k/v: bf16, head h occupies 64 consecutive columns starting at h*64 of its row (d=48: 48 used + 16 pad)
@@ -378,12 +474,19 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
     p.dbg = dbg;
   }
   dim3 grid((Lq + 127) / 128, heads, B * nsplit);
+  p.prof = nullptr;
+  static int prof = -1;
+  if (prof < 0) {
+    const char* e = getenv("XS_ATTN_PROF");
+    prof = e ? atoi(e) : 0;
+  }
+  if (prof) return launch_attn_prof(head_dim, grid, tmQ, tmK, tmV, p, stream);
   if (head_dim == 64) {
-    auto kern = attn_tc_kernel<4, 64>;
+    auto kern = attn_tc_kernel<4, 64, false>;
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
     kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {
-    auto kern = attn_tc_kernel<3, 48>;
+    auto kern = attn_tc_kernel<3, 48, false>;
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
     kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   }

@@ -288,10 +288,8 @@ template <typename AT>
 __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ o_parts,
                                                         const float* __restrict__ lse_parts, AT* __restrict__ out,
                                                         float* __restrict__ lse_out, int R, int B, int Lq, int heads,
-                                                        int d) {
+                                                        int d, long long part_o, long long part_l) {
   const long long total = static_cast<long long>(B) * Lq * heads * d;
-  const long long part_o = total;
-  const long long part_l = static_cast<long long>(B) * heads * Lq;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int e = static_cast<int>(idx % d);
@@ -308,7 +306,7 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
       den += w;
       acc += w * o_parts[s * part_o + idx];
     }
-    const float v = acc / den;
+    const float v = acc / den;  // a part with no keys carries lse = -inf: weight 0 (its O must be finite)
     if constexpr (sizeof(AT) == 2) out[idx] = __float2bfloat16_rn(v);
     else out[idx] = v;
     if (lse_out != nullptr && e == 0) lse_out[li] = mx + logf(den);
@@ -430,12 +428,17 @@ int table_bicubic(const float* in, float* out, int ih, int iw, int oh, int ow, i
 }
 
 int rows_lse_merge(const float* o_parts, const float* lse_parts, void* out, float* lse_out, int R, int B, int Lq,
-                   int heads, int d, int dtype, cudaStream_t stream) {
+                   int heads, int d, long long o_part_stride, long long lse_part_stride, int dtype,
+                   cudaStream_t stream) {
   XS_CHECK_ARG(R > 0 && B > 0 && Lq > 0 && heads > 0 && d > 0, "lse_merge: bad dims");
   const long long total = static_cast<long long>(B) * Lq * heads * d;
-  XS_DISPATCH_AT(dtype, (lse_merge_kernel<AT><<<grid_for(total), 256, 0, stream>>>(o_parts, lse_parts,
-                                                                                   static_cast<AT*>(out), lse_out, R,
-                                                                                   B, Lq, heads, d)));
+  const long long part_l = static_cast<long long>(B) * heads * Lq;
+  if (o_part_stride == 0) o_part_stride = total;
+  if (lse_part_stride == 0) lse_part_stride = part_l;
+  XS_CHECK_ARG(o_part_stride >= total && lse_part_stride >= part_l, "lse_merge: part strides overlap");
+  XS_DISPATCH_AT(dtype, (lse_merge_kernel<AT><<<grid_for(total), 256, 0, stream>>>(
+                            o_parts, lse_parts, static_cast<AT*>(out), lse_out, R, B, Lq, heads, d, o_part_stride,
+                            lse_part_stride)));
   XS_LAUNCH_CHECK();
   return 0;
 }

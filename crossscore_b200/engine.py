@@ -245,7 +245,7 @@ class Engine:
                 call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o_parts), _ptr(l_parts), B, heads, Lq, Lk, d,
                      slot, q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), nsplit, 1, scale, self.dt, st)
             with self._op("lse_merge", 0.0, o_parts.numel() * 4.0):
-                call("xs_lse_merge", _ptr(o_parts), _ptr(l_parts), _ptr(o), _ptr(lse), nsplit, B, Lq, heads, d,
+                call("xs_lse_merge", _ptr(o_parts), _ptr(l_parts), _ptr(o), _ptr(lse), nsplit, B, Lq, heads, d, 0, 0,
                      DT_F32 if o_is_f32 else DT_BF16, st)
 
     # ---- DINOv2 backbone over a list of image tensors (each (n,3,H,W) fp32, same H,W) --------------
@@ -350,11 +350,11 @@ class Engine:
                 self._gemm(att, D["sa_wo"], D["sa_bo"], d, ACT_NONE, st, tag="gemm_dec")
                 self._ln(xq32 if sc else None, d, None, D["ln1_g"], D["ln1_b"], DEC_EPS, None, xq32, R, st)
             self._gemm(xq32, D["ca_wq"], D["ca_bq"], qc, ACT_NONE, st, tag="gemm_dec", n_real=C)
-            k_view, v_view = kv[:, l * 2 * E:], kv[:, l * 2 * E + E:]
             last = need_attn_weights and l == DEC_LAYERS - 1
             if cross_attn_fn is not None:
                 cross_attn_fn(l, qc, att, lse if last else None, st)
             else:
+                k_view, v_view = kv[:, l * 2 * E:], kv[:, l * 2 * E + E:]
                 self._attn(qc, k_view, v_view, att, B, DEC_HEADS, P, M, DEC_D, slot, E, P * E, 4 * E, M * 4 * E,
                            kv_shared, st, lse=lse if last else None, name="dca")
             self._gemm(att, D["ca_wo"], D["ca_bo"], d, ACT_NONE, st, tag="gemm_dec")
@@ -378,6 +378,27 @@ class Engine:
                  _ptr(score), B, ph, pw, C, int(self.use_tanh), self.power,
                  DT_TF32 if self.dt == DT_BF16 else DT_F32, st)
         return score, probs
+
+    # ---- split-KV pieces used by crossscore_b200.scene.SplitKVScorer -------------------------------------
+    @property
+    def kv_width(self):
+        return 4 * self.w.E
+
+    def cross_attn_partial(self, layer, qc, kv_local, B, P, M_local, packed, st):
+        """Cross-attention of decoder layer `layer` over THIS rank's keys only.  packed (fp32, 1-D) receives the
+        normalised partial O (B*P*C) followed by LSE (B*8*P) -- the unit one all-gather moves per layer."""
+        E, slot = self.w.E, self.w.slot
+        o = packed[:B * P * C].view(B * P, C)
+        lse = packed[B * P * C:B * P * C + B * DEC_HEADS * P].view(B, DEC_HEADS, P)
+        self._attn(qc, kv_local[:, layer * 2 * E:], kv_local[:, layer * 2 * E + E:], o, B, DEC_HEADS, P, M_local,
+                   DEC_D, slot, E, P * E, 4 * E, M_local * 4 * E, False, st, lse=lse, name="dca_part")
+
+    def merge_partials(self, gathered, n_parts, B, P, att, lse_out, st):
+        """gathered: n_parts packed (O_r | LSE_r) buffers back to back -> att (B*P, C) fp32 (+ merged LSE)."""
+        part = B * P * C + B * DEC_HEADS * P
+        with self._op("lse_merge", 0.0, n_parts * part * 4.0 + att.numel() * 4.0):
+            call("xs_lse_merge", _ptr(gathered), gathered.data_ptr() + B * P * C * 4, _ptr(att), _ptr(lse_out),
+                 n_parts, B, P, DEC_HEADS, DEC_D, part, part, DT_F32, st)
 
     # ---- the reference-shaped forward ------------------------------------------------------------
     def forward(self, query_img, ref_imgs, need_attn_weights=False, head_id=0):

@@ -111,9 +111,14 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
                   float scale, int dtype, xs_stream_t stream);
 
 /* C2  split-KV merge: LSE = log sum_r exp(LSE_r), O = sum_r exp(LSE_r - LSE) O_r  (no reference counterpart;
- *     identity in SURVEY.md appendix B-10).  Parts may come from local splits or an NCCL all-gather. */
+ *     identity in SURVEY.md appendix B-10).  Parts may come from local splits or an NCCL all-gather:
+ *     part r of O starts at o_parts + r*o_part_stride, of LSE at lse_parts + r*lse_part_stride (floats;
+ *     0 = dense [n_parts][B*Lq][heads*head_dim] / [n_parts][B][heads][Lq]), so one packed all-gather
+ *     buffer holding (O_r | LSE_r) per rank merges in place.  A part that saw no keys carries LSE = -inf
+ *     and a finite O; it contributes nothing. */
 int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float* lse_out, int n_parts, int B,
-                 int Lq, int heads, int head_dim, int dtype, xs_stream_t stream);
+                 int Lq, int heads, int head_dim, long long o_part_stride, long long lse_part_stride, int dtype,
+                 xs_stream_t stream);
 
 /* K12  head[2] Linear(384->196) + Sigmoid/Tanh (+pow) + jigsaw_to_image
  *      (model/cross_reference.py:45-50,82-87; model/regression_layer.py:26-62; utils/misc/image.py:8-21).

@@ -157,7 +157,7 @@ def run_attn(dtype_flag, B, H, Lq, Lk, d, slot, nsplit=1, kv_shared=False, seed=
         mdt = torch.float32 if force_f32_out else adt
         merged = torch.empty(B * Lq, H * d, device=DEV, dtype=mdt)
         lse_m = torch.empty(B, H, Lq, device=DEV)
-        call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d,
+        call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d, 0, 0,
              DT_F32 if mdt == torch.float32 else DT_BF16, st())
         o, lse = merged, lse_m
     else:
