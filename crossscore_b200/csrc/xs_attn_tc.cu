@@ -16,7 +16,7 @@
 // cycles per round trip, several times the MMA cycles of a block) is off the critical path; the softmax
 // warps stream continuously and the kernel runs at the exp (MUFU, 16/clk/SM) bound rather than on latency.
 // Barrier traffic is per warp: lane 0 polls / arrives, __syncwarp broadcasts.
-// TMEM (256 columns, two CTAs per SM): S_b [64b, 64b+64), b = 0..2 (P_b aliases the first 32 columns of S_b),
+// TMEM (256 columns, two CTAs per SM): S_b [64b, 64b+64), b = 0..2 (P_b aliases the last 32 columns of S_b),
 // O [192, 192+DV).
 // Head dim 48 (decoder) uses 64-wide padded head slots in global memory: QK^T issues 3 K-steps (48) and
 // PV uses N=48, so no padded FLOPs are executed.
@@ -31,9 +31,9 @@ namespace xs {
 
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_BKV = 64;                             // keys per block
-constexpr int ATT_ST = 4;                               // K and V ring depth
+constexpr int ATT_ST = 5;                               // K and V ring depth
 constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK runs ATT_NS blocks ahead of PV)
-constexpr float ATT_GROW = 16.0f;                       // log2 headroom of P above the stale row max before a rescale
+constexpr float ATT_SUM_LIMIT = 65536.0f;                // a block row-sum of P above this (vs the stale max) forces a rescale
 constexpr uint32_t ATT_Q_BYTES = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16], 128B swizzle
 constexpr uint32_t ATT_KV_BYTES = ATT_BKV * 64 * 2;     // 8 KB:  [64 keys][64 bf16]
 constexpr uint32_t ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_ST * ATT_KV_BYTES + 256 + 1024;
@@ -80,6 +80,33 @@ struct PhaseClock {
     }
   }
 };
+
+struct MaskNo { static constexpr bool value = false; };
+struct MaskYes { static constexpr bool value = true; };
+
+// columns >= valid of a 32-column chunk of logits -> -inf (ragged tail of the key sequence)
+__device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int valid) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i >= valid) v[i] = 0xff800000u;
+}
+
+// P = exp2(S * scale_log2 - m) for 32 logits of one row, packed to bf16x2; the two float2 accumulators collect
+// the row sum.  Packed fp32x2 FMA / ADD (sm_100 FFMA2 / FADD2) halve the FMA-pipe issue slots next to the
+// MUFU-bound exponentials: per pair 1 FFMA2 + 2 MUFU.EX2 + 1 FADD2 + 1 F2FP.
+__device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], float sl2, float neg_m, uint32_t (&pk)[16],
+                                          float2& acc0, float2& acc1) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 x = ffma2_bcast(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), sl2, neg_m);
+    float2 a;
+    a.x = fast_exp2(x.x);
+    a.y = fast_exp2(x.y);
+    if (i & 1) acc1 = fadd2(acc1, a);
+    else acc0 = fadd2(acc0, a);
+    pk[i] = pack_bf16x2(a.x, a.y);
+  }
+}
 
 template <int DQK_STEPS, int DV, bool PROF>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -187,7 +214,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
-        const uint32_t a_p = tb + sb * 64;
+        const uint32_t a_p = tb + sb * 64 + 32;  // P_j lives in the upper half of S_j
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k) {
           // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
@@ -210,83 +237,75 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t t_o = tmem_O + lane_off;
     const float sl2 = p.scale_log2;
-    float m = -INFINITY;  // running (possibly stale) max, log2 domain
+    float m = -INFINITY;  // reference max of the row (log2 domain); may be stale by up to ATT_GROW
     float l = 0.f;        // running sum of exp2(s - m)
     PhaseClock<PROF> pc;
     pc.start();
 
-    for (int j = 0; j < nkv; ++j) {
+    // Software pipeline: the block is processed as two 32-column chunks (va, vb).  While chunk A is in the
+    // exponentials, the tcgen05.ld of chunk B is in flight; while chunk B is in the exponentials, chunk A of
+    // the NEXT block is in flight (S is triple-buffered, so S_{j+1} is normally complete long before).
+    uint32_t va[32], vb[32];
+    if (lane == 0) mbar_wait(&s_full[0], 0);
+    __syncwarp();
+    tc_fence_after();
+    tmem_ld32(tmem_base + lane_off, va);
+    pc.lap(0);
+
+    auto block = [&](const int j, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
       const int sb = j % ATT_NS;
       const uint32_t t_s = tmem_base + lane_off + sb * 64;
-      if (lane == 0) mbar_wait(&s_full[sb], (j / ATT_NS) & 1);
-      __syncwarp();
-      pc.lap(0);  // waiting for S_j
-      tc_fence_after();
-      if (p.dbg & 4) {  // timing experiment: no softmax work at all
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[sb]);
-        continue;
-      }
-      uint32_t v0[32], v1[32];
-      tmem_ld32(t_s, v0);
-      tmem_ld32(t_s + 32, v1);
-      tmem_ld_wait32(v0);
-      tmem_ld_wait32(v1);
-      pc.lap(1);  // tcgen05.ld of the S block
       const int valid = kv_end - (kv_begin + j * ATT_BKV);  // columns >= valid are past the sequence end
-      if (valid < ATT_BKV) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= valid) v0[i] = 0xff800000u;       // -inf
-          if (32 + i >= valid) v1[i] = 0xff800000u;
-        }
+      uint32_t pka[16], pkb[16];
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      const float neg_m = -m;
+
+      tmem_ld_wait32(va);
+      tmem_ld32(t_s + 32, vb);  // in flight during chunk A
+      pc.lap(1);
+      if constexpr (MASK) mask_tail(va, valid);
+      if (j > 0) exp_chunk(va, sl2, neg_m, pka, acc0, acc1);
+      pc.lap(2);
+      tmem_ld_wait32(vb);
+      pc.lap(6);  // residual wait for chunk B
+      // P_j overwrites the UPPER half of S_j (columns 32..63, all in registers now), so chunk A's P goes out while
+      // chunk B is in the exponentials and S_j's lower half stays intact for the slow path's reload
+      if (j > 0) tmem_st16(t_s + 32, pka);
+      if (j + 1 < nkv) {  // prefetch chunk A of the next block (va is dead until then)
+        const int sn = (j + 1) % ATT_NS;
+        if (lane == 0) mbar_wait(&s_full[sn], ((j + 1) / ATT_NS) & 1);
+        __syncwarp();
+        tc_fence_after();
+        tmem_ld32(tmem_base + lane_off + sn * 64, va);
       }
-      // ---- fused pass: P = exp2(S*scale - m) with the STALE running max m, while the max of THIS block is
-      // reduced on the ALU pipe in the shadow of the MUFU-bound exponentials.  (A separate max pass in front
-      // of the exponentials serialises two phases per warp, and the two co-resident CTAs' softmax warps fall
-      // into lock-step on the shared MUFU: measured 1083 clk per 128x64 block per SM vs the 512 clk MUFU
-      // bound.)  Exactness does not depend on m: any m gives the same softmax as long as 2^(s-m) stays in
-      // range (bf16 P and the fp32 sums keep their relative precision at any magnitude), so P is only recomputed
-      // when some row's block max exceeds m by more than ATT_GROW, which bounds P by 2^ATT_GROW and l by
-      // Lk * 2^ATT_GROW; the first block (m = -inf) always takes that path.
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      uint32_t pk0[16], pk1[16];
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      if (j > 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float s0 = __uint_as_float(v0[2 * i]), s1 = __uint_as_float(v0[2 * i + 1]);
-          const float s2 = __uint_as_float(v1[2 * i]), s3 = __uint_as_float(v1[2 * i + 1]);
-          const float a0 = fast_exp2(fmaf(s0, sl2, -m));
-          const float a1 = fast_exp2(fmaf(s1, sl2, -m));
-          const float b0 = fast_exp2(fmaf(s2, sl2, -m));
-          const float b1 = fast_exp2(fmaf(s3, sl2, -m));
-          mx0 = fmaxf(mx0, s0);
-          mx1 = fmaxf(mx1, s1);
-          mx2 = fmaxf(mx2, s2);
-          mx3 = fmaxf(mx3, s3);
-          l0 += a0;
-          l1 += a1;
-          l2 += b0;
-          l3 += b1;
-          pk0[i] = pack_bf16x2(a0, a1);
-          pk1[i] = pack_bf16x2(b0, b1);
-        }
-      } else {
+      pc.lap(0);
+      if constexpr (MASK) mask_tail(vb, valid - 32);
+      if (j > 0) exp_chunk(vb, sl2, neg_m, pkb, acc0, acc1);
+      float bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+      // The exponentials above used the STALE reference max m: any m gives the same softmax as long as
+      // 2^(s-m) stays in range (bf16 P and the fp32 sums keep their relative precision at any magnitude).
+      // The row max is therefore not tracked on the fast path at all; the block's row sum is the overflow
+      // detector (every P <= bsum): only when it exceeds 2^ATT_GROW (or is inf/NaN: first block, m = -inf) is
+      // the true block max taken, (l, O) rescaled and the block recomputed.
+      const bool need = (j == 0) || !(bsum <= ATT_SUM_LIMIT);
+      if (__any_sync(0xffffffffu, need)) {
+        // ---- slow path ----
+        pc.lap(2);
+        if (j + 1 < nkv) tmem_ld_wait32(va);  // the prefetch must land before va is reused
+        tmem_ld32(t_s, va);                   // S_j chunk A again (nothing of P_j has been stored yet)
+        tmem_ld_wait32(va);
+        if constexpr (MASK) mask_tail(va, valid);
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(v0[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(v1[i]));
-          mx3 = fmaxf(mx3, __uint_as_float(v1[i + 1]));
+          mx0 = fmaxf(mx0, __uint_as_float(va[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(va[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(vb[i]));
+          mx3 = fmaxf(mx3, __uint_as_float(vb[i + 1]));
         }
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
-      const bool need = mx > m + ATT_GROW;  // always true on the first block (m = -inf)
-      if (__any_sync(0xffffffffu, need)) {
-        // ---- slow path: move this row's reference max, rescale (l, O), recompute P for the block ----
-        const float m_new = need ? mx : m;
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+        const float m_new = need ? fmaxf(mx, m) : m;
         const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
         l *= alpha;
         if (j > 0) {
@@ -306,31 +325,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         m = m_new;
-        l0 = l1 = l2 = l3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, -m));
-          const float a1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, -m));
-          const float b0 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, -m));
-          const float b1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, -m));
-          l0 += a0;
-          l1 += a1;
-          l2 += b0;
-          l3 += b1;
-          pk0[i] = pack_bf16x2(a0, a1);
-          pk1[i] = pack_bf16x2(b0, b1);
-        }
+        acc0 = make_float2(0.f, 0.f);
+        acc1 = make_float2(0.f, 0.f);
+        tc_wait_st();  // the early store of the stale P_A must not pass the corrected one
+        exp_chunk(va, sl2, -m, pka, acc0, acc1);
+        tmem_st16(t_s + 32, pka);
+        exp_chunk(vb, sl2, -m, pkb, acc0, acc1);
+        bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        if (j + 1 < nkv) tmem_ld32(tmem_base + lane_off + ((j + 1) % ATT_NS) * 64, va);  // redo the prefetch
+        pc.lap(7);  // slow path total
       }
-      l += (l0 + l1) + (l2 + l3);
-      pc.lap(2);  // max / exp2 / pack (incl. the rare rescale path)
-      tmem_st16(t_s, pk0);
-      tmem_st16(t_s + 16, pk1);
+      l += bsum;
+      pc.lap(2);  // exp2 / pack (incl. the rare rescale path)
+      tmem_st16(t_s + 48, pkb);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
       pc.lap(3);  // tcgen05.st of P + fences + arrive
-    }
+    };
+    for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
+    block(nkv - 1, MaskYes{});
 
     // ---- epilogue: O / l, log-sum-exp ----
     if (lane == 0) mbar_wait(o_full, 0);
@@ -409,10 +424,10 @@ static int launch_attn_prof(int head_dim, dim3 grid, const CUtensorMap& tmQ, con
   XS_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
   const double ctas = double(grid.x) * grid.y * grid.z;
   const int nkv = (p.split_len < p.Lk ? p.split_len : p.Lk + ATT_BKV - 1) / ATT_BKV;
-  fprintf(stderr, "attn prof (clk per CTA, ~%d kv blocks): softmax warp: wait_S %.0f  ld_S %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
-                  "epi %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
+  fprintf(stderr, "attn prof (clk per CTA, ~%d kv blocks): softmax warp: wait_S %.0f  ldA %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
+                  "epi %.0f  ldB %.0f  slow %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
           nkv, h[0] / ctas / 4, h[1] / ctas / 4, h[2] / ctas / 4, h[3] / ctas / 4, h[4] / ctas / 4, h[5] / ctas / 4,
-          h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
+          h[6] / ctas / 4, h[7] / ctas / 4, h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
   return 0;
 }
 

@@ -77,6 +77,32 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, two fp32 lanes per issue slot)
+__device__ __forceinline__ float2 ffma2_bcast(float a0, float a1, float b, float c) {  // (a0, a1) * b + c
+  uint64_t d;
+  asm("{\n"
+      ".reg .b64 a, b, c;\n"
+      "mov.b64 a, {%1, %2};\n"
+      "mov.b64 b, {%3, %3};\n"
+      "mov.b64 c, {%4, %4};\n"
+      "fma.rn.f32x2 %0, a, b, c;\n"
+      "}\n"
+      : "=l"(d)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+  return make_float2(__uint_as_float(static_cast<uint32_t>(d)), __uint_as_float(static_cast<uint32_t>(d >> 32)));
+}
+__device__ __forceinline__ float2 fadd2(float2 x, float2 y) {
+  uint64_t d;
+  asm("{\n"
+      ".reg .b64 a, b;\n"
+      "mov.b64 a, {%1, %2};\n"
+      "mov.b64 b, {%3, %4};\n"
+      "add.rn.f32x2 %0, a, b;\n"
+      "}\n"
+      : "=l"(d)
+      : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
+  return make_float2(__uint_as_float(static_cast<uint32_t>(d)), __uint_as_float(static_cast<uint32_t>(d >> 32)));
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -189,26 +189,52 @@ final_ln_pe_kernel(const float* __restrict__ h, const AT* __restrict__ delta, co
 // im2col for the 14x14/stride-14 patch conv: out[(img*P + p), k], k = c*196 + ky*14 + kx (Conv2d weight order),
 // zero padding for k in [588, Kpad)
 // ---------------------------------------------------------------------------------------------
+// One block = one patch row of one image: the 14 image rows of a channel are staged in shared memory with
+// coalesced loads, then every patch's 196-element (c, ky, kx) segment is written contiguously (one warp per
+// patch segment), so both sides of the copy run at full sector efficiency.
 template <typename AT>
 __global__ void __launch_bounds__(256) im2col14_kernel(const float* __restrict__ img, AT* __restrict__ out, int I,
                                                        int H, int W, int ph, int pw, int Kpad) {
-  const long long total = static_cast<long long>(I) * ph * pw * Kpad;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(idx % Kpad);
-    const long long tok = idx / Kpad;
-    float v = 0.f;
-    if (k < 588) {
-      const int P = ph * pw;
-      const int im = static_cast<int>(tok / P);
-      const int p = static_cast<int>(tok - static_cast<long long>(im) * P);
-      const int r = p / pw, cc = p - r * pw;
-      const int c = k / 196, rem = k - c * 196;
-      const int ky = rem / 14, kx = rem - ky * 14;
-      v = __ldg(img + ((static_cast<size_t>(im) * 3 + c) * H + (14 * r + ky)) * W + 14 * cc + kx);
+  extern __shared__ float im2col_rows[];  // [14][W]
+  const int im = blockIdx.x / ph, r = blockIdx.x - im * ph;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int used = 14 * pw;  // columns of the image row that belong to whole patches
+  AT* orow0 = out + (static_cast<size_t>(im) * ph * pw + static_cast<size_t>(r) * pw) * Kpad;
+  for (int c = 0; c < 3; ++c) {
+    const float* src = img + ((static_cast<size_t>(im) * 3 + c) * H + 14 * r) * W;
+    __syncthreads();  // previous channel's readers are done
+    for (int e = threadIdx.x; e < 14 * used; e += 256) {
+      const int ky = e / used, x = e - ky * used;
+      im2col_rows[ky * W + x] = __ldg(src + static_cast<size_t>(ky) * W + x);
     }
-    if constexpr (sizeof(AT) == 2) out[idx] = __float2bfloat16_rn(v);
-    else out[idx] = v;
+    __syncthreads();
+    for (int pc = warp; pc < pw; pc += 8) {
+      AT* dst = orow0 + static_cast<size_t>(pc) * Kpad + c * 196;
+      const float* s0 = im2col_rows + 14 * pc;
+      if constexpr (sizeof(AT) == 4) {
+        for (int k4 = lane; k4 < 49; k4 += 32) {  // 196 = 49 float4 (segment start is 16-byte aligned)
+          float v[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int k = 4 * k4 + t;
+            const int ky = k / 14;
+            v[t] = s0[ky * W + (k - ky * 14)];
+          }
+          reinterpret_cast<float4*>(dst)[k4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+        for (int k = lane; k < 196; k += 32) {
+          const int ky = k / 14;
+          dst[k] = __float2bfloat16_rn(s0[ky * W + (k - ky * 14)]);
+        }
+      }
+      if (c == 2) {  // zero padding of the K tail
+        for (int k = 588 + lane; k < Kpad; k += 32) {
+          if constexpr (sizeof(AT) == 2) orow0[static_cast<size_t>(pc) * Kpad + k] = __float2bfloat16_rn(0.f);
+          else orow0[static_cast<size_t>(pc) * Kpad + k] = 0.f;
+        }
+      }
+    }
   }
 }
 
@@ -406,9 +432,15 @@ int rows_final_ln_pe(const float* h, const void* delta, const float* gamma, cons
 int rows_im2col14(const float* img, void* out, int I, int H, int W, int Kpad, int dtype, cudaStream_t stream) {
   const int ph = H / 14, pw = W / 14;
   XS_CHECK_ARG(I > 0 && ph > 0 && pw > 0 && Kpad >= 588, "im2col: bad dims I=%d H=%d W=%d Kpad=%d", I, H, W, Kpad);
-  const long long total = static_cast<long long>(I) * ph * pw * Kpad;
-  XS_DISPATCH_AT(dtype, (im2col14_kernel<AT><<<grid_for(total), 256, 0, stream>>>(img, static_cast<AT*>(out), I, H, W,
-                                                                                  ph, pw, Kpad)));
+  const size_t smem = static_cast<size_t>(14) * W * sizeof(float);
+  XS_CHECK_ARG(smem <= 200 * 1024, "im2col: image width %d too large", W);
+  if (dtype == XS_BF16) {
+    XS_CUDA(cudaFuncSetAttribute(im2col14_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    XS_CUDA(cudaFuncSetAttribute(im2col14_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  XS_DISPATCH_AT(dtype, (im2col14_kernel<AT><<<I * ph, 256, smem, stream>>>(img, static_cast<AT*>(out), I, H, W, ph,
+                                                                          pw, Kpad)));
   XS_LAUNCH_CHECK();
   return 0;
 }
