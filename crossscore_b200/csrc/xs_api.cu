@@ -65,7 +65,7 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
   for (int i = 0; i + 1 < rank; ++i) gstrides[i] = strides_bytes[i];
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides, gbox, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swz == SWZ_128B ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swz == SWZ_128B ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == SWZ_64B ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] stride0 %llu box [%u,%u]",

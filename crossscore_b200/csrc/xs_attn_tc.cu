@@ -29,9 +29,11 @@
 
 namespace xs {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 256;                        // warpgroup 0: softmax warps 0..3; warpgroup 1: TMA, MMA, 2 idle
 constexpr int ATT_BKV = 64;                             // keys per block
 constexpr int ATT_ST = 5;                               // K and V ring depth
+constexpr int ATT_REGS_SOFTMAX = 200;                   // setmaxnreg budgets (multiples of 8): 4*200 + 4*56 = 8*128
+constexpr int ATT_REGS_CTRL = 56;
 constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK runs ATT_NS blocks ahead of PV)
 constexpr float ATT_SUM_LIMIT = 65536.0f;                // a block row-sum of P above this (vs the stale max) forces a rescale
 constexpr uint32_t ATT_Q_BYTES = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16], 128B swizzle
@@ -48,7 +50,8 @@ struct AttnParams {
   long long o_row_stride, o_batch_stride, o_split_stride;  // elements
   long long lse_split_stride;
   float scale_log2;
-  int dbg;  // timing experiments only (XS_ATTN_DBG): 4 skip the whole softmax
+  int nq_tiles, n_tiles;  // 128-query tiles per (batch, head, split); total tiles
+  int dbg;                // PROF build only (XS_ATTN_DBG): timing experiments that break the result, see kernel
   unsigned long long* prof;  // XS_ATTN_PROF=1 (PROF instantiation only): per-phase clock totals, see flash_attn_bf16_tc
 };
 
@@ -94,55 +97,99 @@ __device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int valid) {
 // P = exp2(S * scale_log2 - m) for 32 logits of one row, packed to bf16x2; the two float2 accumulators collect
 // the row sum.  Packed fp32x2 FMA / ADD (sm_100 FFMA2 / FADD2) halve the FMA-pipe issue slots next to the
 // MUFU-bound exponentials: per pair 1 FFMA2 + 2 MUFU.EX2 + 1 FADD2 + 1 F2FP.
+template <bool DBG>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], float sl2, float neg_m, uint32_t (&pk)[16],
-                                          float2& acc0, float2& acc1) {
+                                          float2& acc0, float2& acc1, int dbg) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float2 x = ffma2_bcast(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), sl2, neg_m);
     float2 a;
-    a.x = fast_exp2(x.x);
-    a.y = fast_exp2(x.y);
+    if (DBG && (dbg & 8)) {  // timing experiment: no MUFU
+      a = x;
+    } else {
+      a.x = fast_exp2(x.x);
+      a.y = fast_exp2(x.y);
+    }
     if (i & 1) acc1 = fadd2(acc1, a);
     else acc0 = fadd2(acc0, a);
     pk[i] = pack_bf16x2(a.x, a.y);
   }
 }
 
-template <int DQK_STEPS, int DV, bool PROF>
+// v[OFF .. OFF+N) * inv -> N consecutive outputs (16-byte vector stores)
+template <int OFF, int N>
+__device__ __forceinline__ void store_row_f32(float* dst, const uint32_t (&v)[32], float inv) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i)
+    reinterpret_cast<float4*>(dst)[i] =
+        make_float4(__uint_as_float(v[OFF + 4 * i]) * inv, __uint_as_float(v[OFF + 4 * i + 1]) * inv,
+                    __uint_as_float(v[OFF + 4 * i + 2]) * inv, __uint_as_float(v[OFF + 4 * i + 3]) * inv);
+}
+template <int OFF, int N>
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const uint32_t (&v)[32], float inv) {
+#pragma unroll
+  for (int i = 0; i < N / 8; ++i) {
+    uint4 pk;
+    pk.x = pack_bf16x2(__uint_as_float(v[OFF + 8 * i + 0]) * inv, __uint_as_float(v[OFF + 8 * i + 1]) * inv);
+    pk.y = pack_bf16x2(__uint_as_float(v[OFF + 8 * i + 2]) * inv, __uint_as_float(v[OFF + 8 * i + 3]) * inv);
+    pk.z = pack_bf16x2(__uint_as_float(v[OFF + 8 * i + 4]) * inv, __uint_as_float(v[OFF + 8 * i + 5]) * inv);
+    pk.w = pack_bf16x2(__uint_as_float(v[OFF + 8 * i + 6]) * inv, __uint_as_float(v[OFF + 8 * i + 7]) * inv);
+    reinterpret_cast<uint4*>(dst)[i] = pk;
+  }
+}
+
+// Work decomposition of the persistent kernel: tile = (batch, kv split, head, 128-query tile), query tile fastest so
+// the CTAs running at the same time share K/V of a few (batch, head) pairs in L2.
+struct TileCoord {
+  int q0, h, b, split, kv_begin, kv_end, nkv;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, const AttnParams& p) {
+  TileCoord t;
+  const int qt = tile % p.nq_tiles;
+  int r = tile / p.nq_tiles;
+  t.h = r % p.heads;
+  r /= p.heads;
+  t.split = r % p.nsplit;
+  t.b = r / p.nsplit;
+  t.q0 = qt * 128;
+  t.kv_begin = t.split * p.split_len;
+  t.kv_end = min(p.Lk, t.kv_begin + p.split_len);
+  t.nkv = (t.kv_end - t.kv_begin + ATT_BKV - 1) / ATT_BKV;
+  return t;
+}
+
+// MODE 0: production; 1: phase clocks (XS_ATTN_PROF=1); 2: timing experiments that break the result (XS_ATTN_DBG=mask)
+template <int DQK_STEPS, int DV, int MODE>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+  constexpr bool PROF = (MODE & 1) != 0;
+  constexpr bool DBG = (MODE & 2) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smQ = smem;
   uint8_t* smK = smem + ATT_Q_BYTES;
   uint8_t* smV = smK + ATT_ST * ATT_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smV + ATT_ST * ATT_KV_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                // [ATT_ST] K_j and V_j landed
-  uint64_t* kv_empty = kv_full + ATT_ST;       // [ATT_ST] PV_j complete: slot free (also read by the O rescale)
+  uint64_t* q_full = bars + 0;                 // Q tile landed
+  uint64_t* q_empty = bars + 1;                // last QK^T of the tile complete: Q buffer free
+  uint64_t* kv_full = bars + 2;                // [ATT_ST] K_g and V_g landed
+  uint64_t* kv_empty = kv_full + ATT_ST;       // [ATT_ST] PV_g complete: slot free (also read by the O rescale)
   uint64_t* s_full = kv_empty + ATT_ST;        // [ATT_NS]
   uint64_t* p_full = s_full + ATT_NS;          // [ATT_NS]
-  uint64_t* o_full = p_full + ATT_NS;          // all PV complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_full + ATT_NS;          // all PV of the tile complete
+  uint64_t* o_empty = o_full + 1;              // O read out by the softmax warps: next tile's PV_0 may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int q0 = blockIdx.x * 128;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z / p.nsplit;
-  const int split = blockIdx.z - b * p.nsplit;
-  const int kv_begin = split * p.split_len;
-  const int kv_end = min(p.Lk, kv_begin + p.split_len);
-  const int nkv = (kv_end - kv_begin + ATT_BKV - 1) / ATT_BKV;
-  const int b_kv = p.kv_shared ? 0 : b;
-
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < ATT_ST; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -152,34 +199,51 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&p_full[s], 4);  // one arrival per softmax warp
     }
     mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + ATT_NS * 64;
+  // Register budget: the kernel is compiled for 128 registers/thread (2 CTAs x 256 threads); the control
+  // warpgroup gives most of its share back and the softmax warpgroup (two 32-column chunks of logits, two packed
+  // P chunks and a prefetch in flight per thread) takes it.
 
-  if (warp == 0) {
+  // All roles walk the same static tile sequence; `g` counts K/V blocks over the CTA's lifetime (ring slot
+  // g % ATT_ST, S buffer g % ATT_NS and the barrier phases follow from it), `it` counts tiles.
+  if (warp >= 4) reg_dealloc<ATT_REGS_CTRL>();
+  if (warp == 4) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
-    if (elect_one_sync()) {
-      mbar_expect_tx(q_full, ATT_Q_BYTES);
-      tma_load_3d(smQ, &tmQ, q_full, h * 64, q0, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % ATT_ST;
-      const int kv0 = kv_begin + j * ATT_BKV;
-      mbar_wait(&kv_empty[s], ((j / ATT_ST) & 1) ^ 1);
+    uint32_t g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(tile, p);
+      const int b_kv = p.kv_shared ? 0 : t.b;
+      mbar_wait(q_empty, (it & 1) ^ 1);  // previous tile's QK^T are done with the Q buffer
       if (elect_one_sync()) {
-        mbar_expect_tx(&kv_full[s], 2 * ATT_KV_BYTES);
-        tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, &kv_full[s], h * 64, kv0, b_kv);
-        tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, &kv_full[s], h * 64, kv0, b_kv);
+        mbar_expect_tx(q_full, ATT_Q_BYTES);
+        tma_load_3d(smQ, &tmQ, q_full, t.h * 64, t.q0, t.b);
       }
       __syncwarp();
+      for (int j = 0; j < t.nkv; ++j, ++g) {
+        const uint32_t s = g % ATT_ST;
+        const int kv0 = t.kv_begin + j * ATT_BKV;
+        mbar_wait(&kv_empty[s], ((g / ATT_ST) & 1) ^ 1);
+        if (elect_one_sync()) {
+          if (DBG && (p.dbg & 64) && g >= ATT_ST) {  // timing experiment: no K/V traffic after the first ring fill
+            mbar_arrive(&kv_full[s]);
+          } else {
+            mbar_expect_tx(&kv_full[s], 2 * ATT_KV_BYTES);
+            tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, &kv_full[s], t.h * 64, kv0, b_kv);
+            tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, &kv_full[s], t.h * 64, kv0, b_kv);
+          }
+        }
+        __syncwarp();
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BKV, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major ([kv][d], d contiguous)
@@ -187,215 +251,242 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t q_lo = umma_desc_lo(smem_u32(smQ), 16);
     const uint32_t k_lo0 = umma_desc_lo(smem_u32(smK), 16);
     const uint32_t v_lo0 = umma_desc_lo(smem_u32(smV), 1024);
-    auto issue_qk = [&](int jj) {
-      const int s = jj % ATT_ST;
-      mbar_wait(&kv_full[s], (jj / ATT_ST) & 1);  // K_jj (and V_jj) have landed
+    auto issue_qk = [&](uint32_t gg, bool last_of_tile) {
+      const uint32_t s = gg % ATT_ST;
+      mbar_wait(&kv_full[s], (gg / ATT_ST) & 1);  // K_gg (and V_gg) have landed
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
-        const uint32_t d_s = tb + (jj % ATT_NS) * 64;
+        const uint32_t d_s = tb + (gg % ATT_NS) * 64;
 #pragma unroll
         for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[jj % ATT_NS]);
+        tc_commit(&s_full[gg % ATT_NS]);
+        if (last_of_tile) tc_commit(q_empty);  // Q buffer may be refilled once these MMAs have read it
       }
       __syncwarp();
     };
     PhaseClock<PROF> pc;
     pc.start();
-    mbar_wait(q_full, 0);
-    for (int jj = 0; jj < ATT_NS && jj < nkv; ++jj) issue_qk(jj);
-    pc.lap(0);  // prologue: Q + first S blocks issued
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % ATT_ST;
-      const int sb = j % ATT_NS;
-      // softmax has turned S_sb into P_j (and rescaled O if the row max moved)
-      mbar_wait(&p_full[sb], (j / ATT_NS) & 1);
-      pc.lap(1);  // waiting for P_j
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
-        const uint32_t a_p = tb + sb * 64 + 32;  // P_j lives in the upper half of S_j
+    uint32_t g0 = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(tile, p);
+      const int nkv = t.nkv;
+      mbar_wait(q_full, it & 1);
+      // the S buffers of the first blocks are free: the previous tile's PVs were issued before (the tensor pipe
+      // executes in order) and the softmax warps had read those S blocks before they arrived on p_full
+      for (int jj = 0; jj < ATT_NS && jj < nkv; ++jj) issue_qk(g0 + jj, jj == nkv - 1);
+      pc.lap(0);  // prologue: Q + first S blocks issued
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t g = g0 + j;
+        const uint32_t s = g % ATT_ST;
+        const uint32_t sb = g % ATT_NS;
+        // softmax has turned S_sb into P_g (and rescaled O if the row max moved)
+        mbar_wait(&p_full[sb], (g / ATT_NS) & 1);
+        if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);  // previous tile's O has been read out
+        pc.lap(1);  // waiting for P_g
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
+          const uint32_t a_p = tb + sb * 64 + 32;  // P_g lives in the upper half of S_sb
+          if (DBG && (p.dbg & 1)) {  // timing experiment: A operand from smem (the Q tile) instead of P in TMEM
 #pragma unroll
-        for (int k = 0; k < ATT_BKV / 16; ++k) {
-          // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
-          umma_ts_lh(tb + ATT_NS * 64, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < ATT_BKV / 16; ++k)
+              umma_ss_lh<false>(tb + ATT_NS * 64, q_lo + 2 * k, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < ATT_BKV / 16; ++k) {
+              // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
+              umma_ts_lh(tb + ATT_NS * 64, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&kv_empty[s]);  // K_g / V_g slot free; also the "PV_g complete" signal for the O rescale
+          if (j == nkv - 1) tc_commit(o_full);
         }
-        tc_commit(&kv_empty[s]);  // K_j / V_j slot free; also the "PV_j complete" signal for the O rescale
+        __syncwarp();
+        pc.lap(2);  // PV issue
+        if (j + ATT_NS < nkv) issue_qk(g + ATT_NS, j + ATT_NS == nkv - 1);  // overwrites S_sb behind PV_g
+        pc.lap(3);  // K wait + QK issue
       }
-      __syncwarp();
-      pc.lap(2);  // PV_j issue
-      if (j + ATT_NS < nkv) issue_qk(j + ATT_NS);  // overwrites S_sb behind PV_j (tensor pipe executes in order)
-      pc.lap(3);  // K wait + QK_{j+NS} issue
+      g0 += nkv;
     }
-    if (elect_one_sync()) tc_commit(o_full);
-    __syncwarp();
     pc.flush(p.prof, 8, lane);
-  } else if (warp >= 2) {
+  } else if (warp < 4) {
+    reg_alloc<ATT_REGS_SOFTMAX>();
     // ===================== softmax / correction / epilogue (thread == query row) =====================
-    const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+    const int q = warp;  // TMEM lane quarter accessible to this warp (warp id % 4)
     const int row = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t t_o = tmem_O + lane_off;
     const float sl2 = p.scale_log2;
-    float m = -INFINITY;  // reference max of the row (log2 domain); may be stale by up to ATT_GROW
-    float l = 0.f;        // running sum of exp2(s - m)
     PhaseClock<PROF> pc;
     pc.start();
-
-    // Software pipeline: the block is processed as two 32-column chunks (va, vb).  While chunk A is in the
-    // exponentials, the tcgen05.ld of chunk B is in flight; while chunk B is in the exponentials, chunk A of
-    // the NEXT block is in flight (S is triple-buffered, so S_{j+1} is normally complete long before).
-    uint32_t va[32], vb[32];
-    if (lane == 0) mbar_wait(&s_full[0], 0);
-    __syncwarp();
-    tc_fence_after();
-    tmem_ld32(tmem_base + lane_off, va);
-    pc.lap(0);
-
-    auto block = [&](const int j, auto mask_tag) {
-      constexpr bool MASK = decltype(mask_tag)::value;
-      const int sb = j % ATT_NS;
-      const uint32_t t_s = tmem_base + lane_off + sb * 64;
-      const int valid = kv_end - (kv_begin + j * ATT_BKV);  // columns >= valid are past the sequence end
-      uint32_t pka[16], pkb[16];
-      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-      const float neg_m = -m;
-
-      tmem_ld_wait32(va);
-      tmem_ld32(t_s + 32, vb);  // in flight during chunk A
-      pc.lap(1);
-      if constexpr (MASK) mask_tail(va, valid);
-      if (j > 0) exp_chunk(va, sl2, neg_m, pka, acc0, acc1);
-      pc.lap(2);
-      tmem_ld_wait32(vb);
-      pc.lap(6);  // residual wait for chunk B
-      // P_j overwrites the UPPER half of S_j (columns 32..63, all in registers now), so chunk A's P goes out while
-      // chunk B is in the exponentials and S_j's lower half stays intact for the slow path's reload
-      if (j > 0) tmem_st16(t_s + 32, pka);
-      if (j + 1 < nkv) {  // prefetch chunk A of the next block (va is dead until then)
-        const int sn = (j + 1) % ATT_NS;
-        if (lane == 0) mbar_wait(&s_full[sn], ((j + 1) / ATT_NS) & 1);
-        __syncwarp();
-        tc_fence_after();
-        tmem_ld32(tmem_base + lane_off + sn * 64, va);
+    uint32_t g0 = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      int nkv, tail_valid;  // only these two stay live across the block loop (the tile is decoded again for the stores)
+      {
+        const TileCoord t = decode_tile(tile, p);
+        nkv = t.nkv;
+        tail_valid = t.kv_end - t.kv_begin - (t.nkv - 1) * ATT_BKV;  // valid columns of the last block
       }
+      float m = -INFINITY;  // reference max of the row (log2 domain); may be stale (see below)
+      float l = 0.f;        // running sum of exp2(s - m)
+
+      // Software pipeline: a block is processed as two 32-column chunks (va, vb).  While chunk A is in the
+      // exponentials the tcgen05.ld of chunk B is in flight; while chunk B is in the exponentials, chunk A of
+      // the NEXT block is in flight (S is triple-buffered, so S_{g+1} is normally complete long before).
+      uint32_t va[32], vb[32];
+      if (lane == 0) mbar_wait(&s_full[g0 % ATT_NS], (g0 / ATT_NS) & 1);
+      __syncwarp();
+      tc_fence_after();
+      tmem_ld32(tmem_base + lane_off + (g0 % ATT_NS) * 64, va);
       pc.lap(0);
-      if constexpr (MASK) mask_tail(vb, valid - 32);
-      if (j > 0) exp_chunk(vb, sl2, neg_m, pkb, acc0, acc1);
-      float bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-      // The exponentials above used the STALE reference max m: any m gives the same softmax as long as
-      // 2^(s-m) stays in range (bf16 P and the fp32 sums keep their relative precision at any magnitude).
-      // The row max is therefore not tracked on the fast path at all; the block's row sum is the overflow
-      // detector (every P <= bsum): only when it exceeds 2^ATT_GROW (or is inf/NaN: first block, m = -inf) is
-      // the true block max taken, (l, O) rescaled and the block recomputed.
-      const bool need = (j == 0) || !(bsum <= ATT_SUM_LIMIT);
-      if (__any_sync(0xffffffffu, need)) {
-        // ---- slow path ----
-        pc.lap(2);
-        if (j + 1 < nkv) tmem_ld_wait32(va);  // the prefetch must land before va is reused
-        tmem_ld32(t_s, va);                   // S_j chunk A again (nothing of P_j has been stored yet)
+
+      auto block = [&](const int j, auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
+        const uint32_t g = g0 + j;
+        const uint32_t sb = g % ATT_NS;
+        const uint32_t t_s = tmem_base + lane_off + sb * 64;
+        const int valid = tail_valid;  // MASK variant = last block: columns >= valid are past the sequence end
+        uint32_t pka[16], pkb[16];
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        const float neg_m = -m;
+
         tmem_ld_wait32(va);
-        if constexpr (MASK) mask_tail(va, valid);
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(va[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(va[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(vb[i]));
-          mx3 = fmaxf(mx3, __uint_as_float(vb[i + 1]));
+        if (DBG && (p.dbg & 32)) {  // timing experiment: P "ready" before any softmax work (hand-off chain off the critical path)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[sb]);
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
-        const float m_new = need ? fmaxf(mx, m) : m;
-        const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
-        l *= alpha;
-        if (j > 0) {
-          // O must hold PV_0..PV_{j-1}: wait for PV_{j-1} through its K/V slot's kv_empty phase (that slot is
-          // refilled only ATT_ST blocks later, so the parity test cannot alias)
-          if (lane == 0) mbar_wait(&kv_empty[(j - 1) % ATT_ST], ((j - 1) / ATT_ST) & 1);
+        if (!(DBG && (p.dbg & 4))) tmem_ld32(t_s + 32, vb);  // in flight during chunk A   (dbg 4: no S loads)
+        pc.lap(1);
+        if constexpr (MASK) mask_tail(va, valid);
+        if (j > 0) exp_chunk<DBG>(va, sl2, neg_m, pka, acc0, acc1, p.dbg);
+        pc.lap(2);
+        tmem_ld_wait32(vb);
+        pc.lap(6);  // residual wait for chunk B
+        // P_g overwrites the UPPER half of S_sb (columns 32..63, all in registers now), so chunk A's P goes out
+        // while chunk B is in the exponentials and the lower half stays intact for the slow path's reload
+        if (j > 0 && !(DBG && (p.dbg & 2))) tmem_st16(t_s + 32, pka);  // (dbg 2: no P stores)
+        if (j + 1 < nkv) {  // prefetch chunk A of the next block (va is dead until then)
+          const uint32_t sn = (g + 1) % ATT_NS;
+          if (lane == 0) mbar_wait(&s_full[sn], ((g + 1) / ATT_NS) & 1);
           __syncwarp();
           tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < DV / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld16(t_o + c * 16, v);
-            tmem_ld_wait16(v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st16(t_o + c * 16, v);
-          }
+          if (!(DBG && (p.dbg & 4))) tmem_ld32(tmem_base + lane_off + sn * 64, va);
         }
-        m = m_new;
-        acc0 = make_float2(0.f, 0.f);
-        acc1 = make_float2(0.f, 0.f);
-        tc_wait_st();  // the early store of the stale P_A must not pass the corrected one
-        exp_chunk(va, sl2, -m, pka, acc0, acc1);
-        tmem_st16(t_s + 32, pka);
-        exp_chunk(vb, sl2, -m, pkb, acc0, acc1);
-        bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-        if (j + 1 < nkv) tmem_ld32(tmem_base + lane_off + ((j + 1) % ATT_NS) * 64, va);  // redo the prefetch
-        pc.lap(7);  // slow path total
-      }
-      l += bsum;
-      pc.lap(2);  // exp2 / pack (incl. the rare rescale path)
-      tmem_st16(t_s + 48, pkb);
-      tc_wait_st();
+        pc.lap(0);
+        if constexpr (MASK) mask_tail(vb, valid - 32);
+        if (j > 0) exp_chunk<DBG>(vb, sl2, neg_m, pkb, acc0, acc1, p.dbg);
+        float bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+        // The exponentials above used the STALE reference max m: any m gives the same softmax as long as
+        // 2^(s-m) stays in range (bf16 P and the fp32 sums keep their relative precision at any magnitude).
+        // The row max is therefore not tracked on the fast path at all; the block's row sum is the overflow
+        // detector (every P <= bsum): only when it exceeds ATT_SUM_LIMIT (or is inf/NaN) is the true block max
+        // taken, (l, O) rescaled and the block recomputed.  The first block of a tile always takes this path.
+        const bool need = (j == 0) || (!(bsum <= ATT_SUM_LIMIT) && !(DBG && p.dbg));
+        if (__any_sync(0xffffffffu, need)) {
+          pc.lap(2);
+          if (j + 1 < nkv) tmem_ld_wait32(va);  // the prefetch must land before va is reused
+          tmem_ld32(t_s, va);                   // S chunk A again (its columns have not been overwritten)
+          tmem_ld_wait32(va);
+          if constexpr (MASK) mask_tail(va, valid);
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(va[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(va[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(vb[i]));
+            mx3 = fmaxf(mx3, __uint_as_float(vb[i + 1]));
+          }
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+          const float m_new = need ? fmaxf(mx, m) : m;
+          const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
+          l *= alpha;
+          if (j > 0) {
+            // O must hold PV of all earlier blocks of this tile: wait for the previous block's PV through its
+            // K/V slot's kv_empty phase (the slot is refilled only ATT_ST blocks later: the parity cannot alias)
+            if (lane == 0) mbar_wait(&kv_empty[(g - 1) % ATT_ST], ((g - 1) / ATT_ST) & 1);
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < DV / 16; ++c) {
+              uint32_t v[16];
+              tmem_ld16(t_o + c * 16, v);
+              tmem_ld_wait16(v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st16(t_o + c * 16, v);
+            }
+          }
+          m = m_new;
+          acc0 = make_float2(0.f, 0.f);
+          acc1 = make_float2(0.f, 0.f);
+          tc_wait_st();  // the early store of the stale P_A must not pass the corrected one
+          exp_chunk<false>(va, sl2, -m, pka, acc0, acc1, 0);
+          tmem_st16(t_s + 32, pka);
+          exp_chunk<false>(vb, sl2, -m, pkb, acc0, acc1, 0);
+          bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+          if (j + 1 < nkv) tmem_ld32(tmem_base + lane_off + ((g + 1) % ATT_NS) * 64, va);  // redo the prefetch
+          pc.lap(7);  // slow path total
+        }
+        l += bsum;
+        pc.lap(2);  // exp2 / pack
+        if (!(DBG && (p.dbg & 2))) tmem_st16(t_s + 48, pkb);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && !(DBG && (p.dbg & 32))) mbar_arrive(&p_full[sb]);
+        pc.lap(3);  // tcgen05.st of P + fences + arrive
+      };
+      for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
+      block(nkv - 1, MaskYes{});
+      g0 += nkv;
+
+      // ---- epilogue: read O out of TMEM (frees it for the next tile's PV_0), then O / l and log-sum-exp ----
+      if (lane == 0) mbar_wait(o_full, it & 1);
+      __syncwarp();
+      pc.lap(4);  // waiting for the last PV
+      tc_fence_after();
+      tmem_ld32(t_o, va);
+      if constexpr (DV == 64) tmem_ld32(t_o + 32, vb);
+      else tmem_ld16_lo(t_o + 32, vb);  // DV == 48
+      tmem_ld_wait32(va);
+      tmem_ld_wait32(vb);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[sb]);
-      pc.lap(3);  // tcgen05.st of P + fences + arrive
-    };
-    for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
-    block(nkv - 1, MaskYes{});
-
-    // ---- epilogue: O / l, log-sum-exp ----
-    if (lane == 0) mbar_wait(o_full, 0);
-    __syncwarp();
-    pc.lap(4);  // waiting for the last PV
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    const int row_g = q0 + row;
-    const bool row_ok = row_g < p.Lq;
-    const long long o_off = static_cast<long long>(split) * p.o_split_stride +
-                            static_cast<long long>(b) * p.o_batch_stride +
-                            static_cast<long long>(row_g) * p.o_row_stride + static_cast<long long>(h) * DV;
-#pragma unroll
-    for (int c = 0; c < DV / 16; ++c) {
-      uint32_t v[16];
-      tmem_ld16(t_o + c * 16, v);
-      tmem_ld_wait16(v);
+      if (lane == 0) mbar_arrive(o_empty);
+      const float inv = 1.0f / l;
+      const TileCoord t = decode_tile(tile, p);
+      const int row_g = t.q0 + row;
+      const bool row_ok = row_g < p.Lq;
+      const long long o_off = static_cast<long long>(t.split) * p.o_split_stride +
+                              static_cast<long long>(t.b) * p.o_batch_stride +
+                              static_cast<long long>(row_g) * p.o_row_stride + static_cast<long long>(t.h) * DV;
       if (row_ok) {
         if (p.o_is_f32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.o) + o_off + c * 16);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]) * inv, __uint_as_float(v[4 * i + 1]) * inv,
-                                 __uint_as_float(v[4 * i + 2]) * inv, __uint_as_float(v[4 * i + 3]) * inv);
+          float* dst = reinterpret_cast<float*>(p.o) + o_off;
+          store_row_f32<0, 32>(dst, va, inv);
+          store_row_f32<0, DV - 32>(dst + 32, vb, inv);
         } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.o) + o_off + c * 16);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
-            pk.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
-            pk.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
-            pk.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
-            dst[i] = pk;
-          }
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.o) + o_off;
+          store_row_bf16<0, 32>(dst, va, inv);
+          store_row_bf16<0, DV - 32>(dst + 32, vb, inv);
+        }
+        if (p.lse != nullptr) {
+          // natural-log LSE of the scaled logits: ln sum_j exp(s_j * scale)
+          p.lse[static_cast<long long>(t.split) * p.lse_split_stride +
+                (static_cast<long long>(t.b) * p.heads + t.h) * p.Lq + row_g] = (m + log2f(l)) * 0.6931471805599453f;
         }
       }
+      pc.lap(5);  // epilogue stores
     }
-    if (p.lse != nullptr && row_ok) {
-      // natural-log LSE of the scaled logits: ln sum_j exp(s_j * scale)
-      p.lse[static_cast<long long>(split) * p.lse_split_stride +
-            (static_cast<long long>(b) * p.heads + h) * p.Lq + row_g] = (m + log2f(l)) * 0.6931471805599453f;
-    }
-    pc.lap(5);  // epilogue stores
     pc.flush(p.prof, 0, lane);
+    pc.flush(p.prof, 16 + 8 * warp, lane);  // per lane-quarter copy
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -406,28 +497,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 static int launch_attn_prof(int head_dim, dim3 grid, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                             const CUtensorMap& tmV, AttnParams p, cudaStream_t stream) {
   static unsigned long long* buf = nullptr;
-  if (buf == nullptr) XS_CUDA(cudaMalloc(&buf, 16 * sizeof(unsigned long long)));
-  XS_CUDA(cudaMemsetAsync(buf, 0, 16 * sizeof(unsigned long long), stream));
+  if (buf == nullptr) XS_CUDA(cudaMalloc(&buf, 48 * sizeof(unsigned long long)));
+  XS_CUDA(cudaMemsetAsync(buf, 0, 48 * sizeof(unsigned long long), stream));
   p.prof = buf;
-  if (head_dim == 64) {
-    auto kern = attn_tc_kernel<4, 64, true>;
+  if (head_dim == 64 && p.dbg) {
+    auto kern = attn_tc_kernel<4, 64, 3>;
+    XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+    kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  } else if (head_dim == 64) {
+    auto kern = attn_tc_kernel<4, 64, 1>;
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
     kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {
-    auto kern = attn_tc_kernel<3, 48, true>;
+    auto kern = attn_tc_kernel<3, 48, 1>;
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
     kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   }
   XS_LAUNCH_CHECK();
   XS_CUDA(cudaStreamSynchronize(stream));
-  unsigned long long h[16];
+  unsigned long long h[48];
   XS_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
-  const double ctas = double(grid.x) * grid.y * grid.z;
+  const double ctas = double(p.n_tiles);  // per 128-query tile
   const int nkv = (p.split_len < p.Lk ? p.split_len : p.Lk + ATT_BKV - 1) / ATT_BKV;
-  fprintf(stderr, "attn prof (clk per CTA, ~%d kv blocks): softmax warp: wait_S %.0f  ldA %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
+  fprintf(stderr, "attn prof (clk per tile, ~%d kv blocks): softmax warp: wait_S %.0f  ldA %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
                   "epi %.0f  ldB %.0f  slow %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
           nkv, h[0] / ctas / 4, h[1] / ctas / 4, h[2] / ctas / 4, h[3] / ctas / 4, h[4] / ctas / 4, h[5] / ctas / 4,
           h[6] / ctas / 4, h[7] / ctas / 4, h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
+  for (int w = 0; w < 4; ++w) {
+    const unsigned long long* g = h + 16 + 8 * w;
+    fprintf(stderr, "  softmax warp %d: wait_S %.0f  ldA %.0f  exp %.0f  st_P %.0f  wait_O %.0f  epi %.0f  ldB %.0f  slow %.0f\n", w,
+            g[0] / ctas, g[1] / ctas, g[2] / ctas, g[3] / ctas, g[4] / ctas, g[5] / ctas, g[6] / ctas, g[7] / ctas);
+  }
   return 0;
 }
 
@@ -480,28 +580,37 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
   p.o_split_stride = (long long)B * p.o_batch_stride;
   p.lse_split_stride = (long long)B * heads * Lq;
   p.scale_log2 = scale * 1.4426950408889634f;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("XS_ATTN_DBG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.dbg = dbg;
-  }
-  dim3 grid((Lq + 127) / 128, heads, B * nsplit);
+  p.nq_tiles = (Lq + 127) / 128;
+  p.n_tiles = p.nq_tiles * heads * B * nsplit;
+  const int max_ctas = 2 * num_sms();  // two co-resident CTAs per SM, each walking its share of the tiles
+  dim3 grid(p.n_tiles < max_ctas ? p.n_tiles : max_ctas);
   p.prof = nullptr;
+  p.dbg = 0;
   static int prof = -1;
   if (prof < 0) {
     const char* e = getenv("XS_ATTN_PROF");
     prof = e ? atoi(e) : 0;
   }
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("XS_ATTN_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (head_dim == 64) p.dbg = dbg;
+  if (dbg && !prof && head_dim == 64) {  // development: timing experiments on the d=64 shape
+    auto kern = attn_tc_kernel<4, 64, 2>;
+    XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+    kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    XS_LAUNCH_CHECK();
+    return 0;
+  }
   if (prof) return launch_attn_prof(head_dim, grid, tmQ, tmK, tmV, p, stream);
   if (head_dim == 64) {
-    auto kern = attn_tc_kernel<4, 64, false>;
+    auto kern = attn_tc_kernel<4, 64, 0>;
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
     kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   } else {
-    auto kern = attn_tc_kernel<3, 48, false>;
+    auto kern = attn_tc_kernel<3, 48, 0>;
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
     kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   }

@@ -44,7 +44,7 @@ int num_sms();
 
 // host: build TMA descriptors through the driver entry point obtained from cudart (no -lcuda)
 // rank-2: dims {inner, outer}; rank-3: dims {inner, mid, outer}; strides in BYTES for dims 1..rank-1
-enum Swizzle : int { SWZ_NONE = 0, SWZ_128B = 3 };
+enum Swizzle : int { SWZ_NONE = 0, SWZ_64B = 2, SWZ_128B = 3 };
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, Swizzle swz);
 
@@ -162,7 +162,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Spin on the phase bit.  try_wait parks the warp in hardware for up to the suspend-time hint, so the loop
 // issues few instructions.  A pipeline bug would otherwise hang the GPU box until the job limit, so the wait
 // traps after a few seconds (clock checked every 4096 polls) and the host sees a launch failure instead.
+#ifndef XS_MBAR_HINT_NS
+#define XS_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+#if XS_MBAR_HINT_NS == 0
+  return mbar_try_wait(bar, parity);  // default (implementation-defined, short) suspend
+#else
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -171,28 +177,23 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)XS_MBAR_HINT_NS)
       : "memory");
   return ok != 0;
+#endif
 }
-static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    for (int i = 0; i < 4096; ++i)
-      if (mbar_try_wait_hint(bar, parity)) return;
-    if (clock64() - t0 > 8000000000LL) {
-      printf("xs: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
+// Fully inline (no calls: a call inside a setmaxnreg-raised region would pin that region to the kernel-wide
+// register cap).  A pipeline bug traps after a few seconds instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
 #pragma unroll 1
-  for (int i = 0; i < 64; ++i)
-    if (mbar_try_wait_hint(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i)
+      if (mbar_try_wait_hint(bar, parity)) return;
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -232,6 +233,16 @@ __device__ __forceinline__ void tma_store_wait_all() {
 // make generic-proxy smem writes visible to the async proxy (TMA store / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// per-warpgroup register re-budgeting (all warps of the warpgroup execute it)
+template <int REGS>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template <int REGS>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -382,6 +393,72 @@ __device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uin
       : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA spans two SMs, each CTA stages its own A rows and
+// half of the B rows, so the shared-memory fill traffic per output tile drops by a third.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // possibly remote barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {  // same warp id in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to `bar_cluster_addr`
+// (the leader CTA's mbarrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs once all prior MMAs of this thread completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; issued by the leader CTA only
+__device__ __forceinline__ void umma_ss_lh_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -409,6 +486,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 16 columns into the low half of a 32-register buffer
+__device__ __forceinline__ void tmem_ld16_lo(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"

@@ -18,6 +18,8 @@
 // Reference call sites replaced: every torch.nn.Linear / Conv2d(k=s=14) on the path
 // ($SP/transformers/models/dinov2/modeling_dinov2.py:139-149,199-213,246-252,317-327;
 //  model/customised_transformer/transformer.py:68-75,208-210; $SP/torch/nn/functional.py:5849-5858,6692).
+#include <stdlib.h>
+
 #include "xs_common.cuh"
 
 namespace xs {
@@ -28,6 +30,7 @@ constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_THREADS = 256;
 constexpr int ACC_STAGE_COLS = 256;  // TMEM column offset between the two accumulator stages
 constexpr int JIG_LD = 197;          // padded row length of the fp32 score staging tile
+constexpr uint32_t EPI_WARP_STAGE_BYTES = 32 * 128;  // one 32-row staging tile of an epilogue warp (128-byte rows max)
 
 enum Epi : int { EPI_STORE = 0, EPI_JIGSAW = 1 };
 enum InT : int { IN_BF16 = 0, IN_TF32 = 1 };
@@ -43,11 +46,11 @@ struct JigsawParams {
   float power;
 };
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int CTA2 = 0>
 struct GemmSmem {
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
-  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 2 * GEMM_BM * 128 : GEMM_BM * JIG_LD * 4;
+  static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * GEMM_BK * 2;  // a CTA pair splits the W tile rows
+  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * EPI_WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4;
   static constexpr uint32_t OFF_A = 0;
   static constexpr uint32_t OFF_B = OFF_A + STAGES * A_BYTES;
   static constexpr uint32_t OFF_STAGING = OFF_B + STAGES * B_BYTES;
@@ -56,12 +59,22 @@ struct GemmSmem {
   static constexpr uint32_t TOTAL = OFF_BAR + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment of the base
 };
 
-template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT>
+// CTA2 = 1: CTA pairs (cluster of 2, tcgen05 cta_group::2).  One MMA covers a 256 x BN tile: CTA r of the pair
+// stages rows [128 r, 128 r + 128) of A and rows [BN/2 r, BN/2 r + BN/2) of the W tile in ITS shared memory and
+// holds its 128 accumulator rows in ITS TMEM; the leader CTA (rank 0) issues the MMAs, whose completion is
+// multicast to both CTAs' barriers.  Shared-memory fill traffic per output element falls by a third, which is
+// what bounds these K = 384 GEMMs (L2 -> SM bandwidth), see DESIGN.md.
+template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
                JigsawParams jp) {
-  using L = GemmSmem<BN, STAGES, EPI>;
+  using L = GemmSmem<BN, STAGES, EPI, CTA2>;
+  static_assert(!CTA2 || (IN == IN_BF16 && EPI == EPI_STORE), "CTA pairs: bf16 store epilogue only");
+  constexpr int NC = CTA2 ? 2 : 1;                       // CTAs per tile
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader
+  const int worker = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int n_workers = CTA2 ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -77,7 +90,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_m = (M + NC * GEMM_BM - 1) / (NC * GEMM_BM);
   const int num_n = N / BN;
   constexpr int BKE = (IN == IN_TF32) ? 32 : 64;  // elements per 128-byte smem row
   const int num_k = (K + BKE - 1) / BKE;
@@ -93,40 +106,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);  // one elected lane per epilogue warp
+      mbar_init(&tmem_empty[s], 8 * NC);  // one elected lane per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) {
+    if constexpr (CTA2) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // barrier inits and TMEM of both CTAs are in place
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += n_workers) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
-          mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
-          tma_load_2d(smA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BKE, m_blk * GEMM_BM);
-          tma_load_2d(smB + stage * L::B_BYTES, &tmW, &full_bar[stage], kb * BKE, n_blk * BN);
+          if constexpr (CTA2) {
+            // both CTAs' bytes are credited to the LEADER's full barrier (its expect_tx covers the pair)
+            const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (L::A_BYTES + L::B_BYTES));
+            tma_load_2d_pair(smA + stage * L::A_BYTES, &tmA, full_leader, kb * BKE,
+                             (m_blk * 2 + static_cast<int>(rank)) * GEMM_BM);
+            tma_load_2d_pair(smB + stage * L::B_BYTES, &tmW, full_leader, kb * BKE,
+                             n_blk * BN + static_cast<int>(rank) * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], L::A_BYTES + L::B_BYTES);
+            tma_load_2d(smA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BKE, m_blk * GEMM_BM);
+            tma_load_2d(smB + stage * L::B_BYTES, &tmW, &full_bar[stage], kb * BKE, n_blk * BN);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
-    constexpr uint32_t idesc = (IN == IN_TF32) ? umma_idesc_tf32(GEMM_BM, BN) : umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+    constexpr uint32_t idesc =
+        (IN == IN_TF32) ? umma_idesc_tf32(GEMM_BM, BN) : umma_idesc_bf16(NC * GEMM_BM, BN, 0, 0);
     const uint32_t tb = warp_uniform(tmem_base);
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA), 16);
     const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB), 16);
     uint32_t stage = 0, phase = 0, acc_stage = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += n_workers) {
       mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tb + acc_stage * ACC_STAGE_COLS;
@@ -136,11 +164,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + stage * (L::A_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + stage * (L::B_BYTES >> 4);
+          if constexpr (CTA2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row (16 bf16 or 8 tf32 each)
-            umma_ss_lh<IN == IN_TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (kb == num_k - 1) tc_commit(&tmem_full[acc_stage]);  // accumulator complete -> epilogue
+            for (int k = 0; k < 4; ++k)
+              umma_ss_lh_pair(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_pair(&empty_bar[stage]);  // frees the slot in BOTH CTAs
+            if (kb == num_k - 1) tc_commit_pair(&tmem_full[acc_stage]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 4 x 32 bytes of K per 128-byte row (16 bf16 or 8 tf32 each)
+              umma_ss_lh<IN == IN_TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kb == num_k - 1) tc_commit(&tmem_full[acc_stage]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -156,72 +192,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;          // row of the tile owned by this thread
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t chunk_counter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = worker; tile < num_tiles; tile += n_workers) {
+      const int m_blk = (tile / num_n) * NC + static_cast<int>(rank), n_blk = tile % num_n;
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc_stage * ACC_STAGE_COLS + (static_cast<uint32_t>(q * 32) << 16);
 
       if constexpr (EPI == EPI_STORE) {
-        constexpr int CW = (OUT == OUT_F32) ? 32 : 64;  // columns per 128-byte staging row
-        constexpr int HV = CW / 2;                       // accumulator values per thread per chunk
-        constexpr int NCHUNK = BN / CW;
-#pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
-          const uint32_t buf = chunk_counter & 1;
-          ++chunk_counter;
-          // the TMA store that last read this staging buffer (two chunks ago) must have drained
-          if (epi_tid == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, EPI_THREADS);
-          uint32_t v[HV];
-          if constexpr (HV == 32) tmem_ld32(taddr0 + c * CW + half * HV, v);
-          else tmem_ld16(taddr0 + c * CW + half * HV, v);
-          tc_wait_ld();
-          if (c == NCHUNK - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+        // Every epilogue warp works on its own: 32 accumulator columns per step (steps alternate between the two
+        // warps of a lane quarter), own double-buffered 32-row staging tile, own TMA stores.  No block-level
+        // barrier; the tcgen05.ld of the next step is in flight while the current one is converted and stored.
+        constexpr int NSTEP = BN / 32;
+        constexpr int MY_STEPS = NSTEP / 2;
+        static_assert(NSTEP % 2 == 0, "BN must be a multiple of 64");
+        uint8_t* my_staging = staging + (warp - 4) * (2 * EPI_WARP_STAGE_BYTES);
+        const int m0 = m_blk * GEMM_BM + q * 32;
+        uint32_t v[2][32];
+        tmem_ld32(taddr0 + half * 32, v[0]);
+#pragma unroll
+        for (int i = 0; i < MY_STEPS; ++i) {
+          const int c = 2 * i + half;  // this warp's i-th 32-column step
+          tmem_ld_wait32(v[i & 1]);
+          if (i + 1 < MY_STEPS) {
+            tmem_ld32(taddr0 + (c + 2) * 32, v[(i + 1) & 1]);
+          } else {  // accumulator fully read by this warp: hand the TMEM stage back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
+            if (lane == 0) {
+              if constexpr (CTA2) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc_stage]), 0));
+              else mbar_arrive(&tmem_empty[acc_stage]);
+            }
           }
-          const int n0 = n_blk * BN + c * CW;
-          uint8_t* srow = staging + buf * (GEMM_BM * 128) + row * 128;
-          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + half * HV);
-          // 128B swizzle: 16-byte chunk index XOR (row mod 8); conflict-free for thread==row writes
+          const uint32_t buf = chunk_counter & 1;
+          ++chunk_counter;
+          // the TMA store that last read this staging buffer (two steps ago) must have drained
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const int n0 = n_blk * BN + c * 32;
+          uint8_t* srow = my_staging + buf * EPI_WARP_STAGE_BYTES;
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+          const uint32_t(&vv)[32] = v[i & 1];
           if constexpr (OUT == OUT_BF16) {
+            // 64-byte rows, 64B swizzle: 16-byte chunk index XOR ((row >> 1) & 3); conflict-free for thread == row
+            uint8_t* rp = srow + lane * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 ba = __ldg(b4 + j * 2), bb = __ldg(b4 + j * 2 + 1);
               const int o = j * 8;
-              const float x0 = apply_act<ACT>(__uint_as_float(v[o + 0]) + ba.x);
-              const float x1 = apply_act<ACT>(__uint_as_float(v[o + 1]) + ba.y);
-              const float x2 = apply_act<ACT>(__uint_as_float(v[o + 2]) + ba.z);
-              const float x3 = apply_act<ACT>(__uint_as_float(v[o + 3]) + ba.w);
-              const float x4 = apply_act<ACT>(__uint_as_float(v[o + 4]) + bb.x);
-              const float x5 = apply_act<ACT>(__uint_as_float(v[o + 5]) + bb.y);
-              const float x6 = apply_act<ACT>(__uint_as_float(v[o + 6]) + bb.z);
-              const float x7 = apply_act<ACT>(__uint_as_float(v[o + 7]) + bb.w);
               uint4 pk;
-              pk.x = pack_bf16x2(x0, x1);
-              pk.y = pack_bf16x2(x2, x3);
-              pk.z = pack_bf16x2(x4, x5);
-              pk.w = pack_bf16x2(x6, x7);
-              *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = pk;
+              pk.x = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 0]) + ba.x),
+                                 apply_act<ACT>(__uint_as_float(vv[o + 1]) + ba.y));
+              pk.y = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 2]) + ba.z),
+                                 apply_act<ACT>(__uint_as_float(vv[o + 3]) + ba.w));
+              pk.z = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 4]) + bb.x),
+                                 apply_act<ACT>(__uint_as_float(vv[o + 5]) + bb.y));
+              pk.w = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 6]) + bb.z),
+                                 apply_act<ACT>(__uint_as_float(vv[o + 7]) + bb.w));
+              *reinterpret_cast<uint4*>(rp + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
             }
           } else {
+            // 128-byte rows, 128B swizzle: 16-byte chunk index XOR (row & 7)
+            uint8_t* rp = srow + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float4 ba = __ldg(b4 + j);
               float4 o4;
-              o4.x = apply_act<ACT>(__uint_as_float(v[j * 4 + 0]) + ba.x);
-              o4.y = apply_act<ACT>(__uint_as_float(v[j * 4 + 1]) + ba.y);
-              o4.z = apply_act<ACT>(__uint_as_float(v[j * 4 + 2]) + ba.z);
-              o4.w = apply_act<ACT>(__uint_as_float(v[j * 4 + 3]) + ba.w);
-              *reinterpret_cast<float4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = o4;
+              o4.x = apply_act<ACT>(__uint_as_float(vv[j * 4 + 0]) + ba.x);
+              o4.y = apply_act<ACT>(__uint_as_float(vv[j * 4 + 1]) + ba.y);
+              o4.z = apply_act<ACT>(__uint_as_float(vv[j * 4 + 2]) + ba.z);
+              o4.w = apply_act<ACT>(__uint_as_float(vv[j * 4 + 3]) + ba.w);
+              *reinterpret_cast<float4*>(rp + ((j ^ (lane & 7)) << 4)) = o4;
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, EPI_THREADS);
-          if (epi_tid == 0) {
-            tma_store_2d(&tmC, staging + buf * (GEMM_BM * 128), n0, m_blk * GEMM_BM);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, srow, n0, m0);  // box = 32 columns x 32 rows; clips the M tail
             tma_store_commit();
           }
         }
@@ -277,25 +323,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (acc_stage == 0) acc_phase ^= 1;
     }
     if constexpr (EPI == EPI_STORE) {
-      if (epi_tid == 0) tma_store_wait_all<0>();
+      if (lane == 0) tma_store_wait_all<0>();
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's smem / TMEM / barriers stay alive until both CTAs are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CTA2) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT>
+template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2 = 0>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                        int N, int K, JigsawParams jp, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES, EPI>;
+  using L = GemmSmem<BN, STAGES, EPI, CTA2>;
   constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
   constexpr int OUT_B = (OUT == OUT_F32) ? 4 : 2;
   constexpr uint32_t BKE = 128 / IN_B;
@@ -310,39 +358,57 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ldw * IN_B};
-    uint32_t box[2] = {BKE, (uint32_t)BN};
+    uint32_t box[2] = {BKE, (uint32_t)(CTA2 ? BN / 2 : BN)};
     int rc = make_tmap(&tmW, W, IN_B, 2, dims, strides, box, SWZ_128B);
     if (rc) return rc;
   }
   if (EPI == EPI_STORE) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)ldc * OUT_B};
-    uint32_t box[2] = {128 / OUT_B, GEMM_BM};
-    int rc = make_tmap(&tmC, out, OUT_B, 2, dims, strides, box, SWZ_128B);
+    uint32_t box[2] = {32, 32};  // one epilogue-warp step: 32 columns x 32 rows (64-byte rows for bf16, 128 for fp32)
+    int rc = make_tmap(&tmC, out, OUT_B, 2, dims, strides, box, OUT_B == 2 ? SWZ_64B : SWZ_128B);
     if (rc) return rc;
   } else {
     tmC = tmA;  // unused
   }
-  auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT, IN, OUT>;
+  auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT, IN, OUT, CTA2>;
   XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
-  const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmW, tmC, bias, M, N, K, jp);
+  if constexpr (CTA2) {
+    const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * (N / BN);
+    const int pairs = num_tiles < num_sms() / 2 ? num_tiles : num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmC, bias, M, N, K, jp));
+  } else {
+    const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmW, tmC, bias, M, N, K, jp);
+  }
   XS_LAUNCH_CHECK();
   return 0;
 }
 
 #define XS_GEMM_ARGS A, lda, W, ldw, bias, out, ldc, M, N, K, jp, stream
 
-template <int BN, int STAGES, int IN, int OUT>
+template <int BN, int STAGES, int IN, int OUT, int CTA2 = 0>
 static int dispatch_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                         int N, int K, int act, cudaStream_t stream) {
   JigsawParams jp{};
   switch (act) {
-    case ACT_NONE: return launch_gemm<BN, STAGES, EPI_STORE, ACT_NONE, IN, OUT>(XS_GEMM_ARGS);
-    case ACT_GELU: return launch_gemm<BN, STAGES, EPI_STORE, ACT_GELU, IN, OUT>(XS_GEMM_ARGS);
-    case ACT_RELU: return launch_gemm<BN, STAGES, EPI_STORE, ACT_RELU, IN, OUT>(XS_GEMM_ARGS);
-    case ACT_LEAKY: return launch_gemm<BN, STAGES, EPI_STORE, ACT_LEAKY, IN, OUT>(XS_GEMM_ARGS);
+    case ACT_NONE: return launch_gemm<BN, STAGES, EPI_STORE, ACT_NONE, IN, OUT, CTA2>(XS_GEMM_ARGS);
+    case ACT_GELU: return launch_gemm<BN, STAGES, EPI_STORE, ACT_GELU, IN, OUT, CTA2>(XS_GEMM_ARGS);
+    case ACT_RELU: return launch_gemm<BN, STAGES, EPI_STORE, ACT_RELU, IN, OUT, CTA2>(XS_GEMM_ARGS);
+    case ACT_LEAKY: return launch_gemm<BN, STAGES, EPI_STORE, ACT_LEAKY, IN, OUT, CTA2>(XS_GEMM_ARGS);
   }
   set_last_error("xs_gemm_bias_act: unknown activation %d", act);
   return -1;
@@ -364,6 +430,21 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
   const bool use192 = (N % 192 == 0) && (N % 256 != 0 || N < 1024);
   XS_CHECK_ARG(use192 || N % 256 == 0, "gemm: N=%d must be a multiple of 192 or 256 (pad the weight rows)", N);
   if (!in_tf32 && !out_f32) {
+    // CTA pairs for the long-K GEMM (fc2, K = 1536: 1.35 PF vs 1.13 PF single-CTA, measured); the K = 384 GEMMs
+    // are bound by their epilogue / operand refill per tile and run faster as independent CTAs.
+    // XS_GEMM_PAIR=0 / 2 forces the single-CTA / pair kernel.
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+      const char* e = getenv("XS_GEMM_PAIR");
+      pair_mode = e ? atoi(e) : 1;
+    }
+    const int bn = use192 ? 192 : 256;
+    const bool fits = ((M + 255) / 256) * (N / bn) >= num_sms() / 2;
+    const bool pair = fits && (pair_mode == 2 || (pair_mode == 1 && K >= 1024));
+    if (pair) {
+      if (use192) return dispatch_act<192, 5, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+      return dispatch_act<256, 5, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+    }
     if (use192) return dispatch_act<192, 4, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
     return dispatch_act<256, 3, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
   }

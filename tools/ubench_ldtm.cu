@@ -9,6 +9,39 @@ namespace xs { void set_last_error(const char*, ...) {} int num_sms() { return 1
 int make_tmap(CUtensorMap*, const void*, int, int, const uint64_t*, const uint64_t*, const uint32_t*, Swizzle) { return 0; } }
 using namespace xs;
 
+
+__device__ __forceinline__ void ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void ld_16x128b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x128b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[32], int o) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[o]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]),
+                 "=r"(r[o + 7])
+               : "r"(taddr)
+               : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512) ubench(int iters, long long* out, int tmem_cols, float* sink) {
   __shared__ uint32_t slot;
@@ -33,6 +66,24 @@ __global__ void __launch_bounds__(512) ubench(int iters, long long* out, int tme
       acc += __uint_as_float(vb[i & 31]);
     } else if (MODE == 2) {
       tmem_ld32(tb + col, va); tmem_ld32(tb + col + 32, vb);
+      tmem_ld_wait32(va); tmem_ld_wait32(vb);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc += fast_exp2(__uint_as_float(va[k]) * 1e-9f) + fast_exp2(__uint_as_float(vb[k]) * 1e-9f);
+    } else if (MODE == 4) {  // 16x256b.x8: 16 lanes x 64 columns per instruction, two instructions per 32-lane block
+      ld_16x256b_x8(tb + col, va); ld_16x256b_x8(tb + col + (16u << 16), vb);
+      tmem_ld_wait32(va); tmem_ld_wait32(vb);
+      acc += __uint_as_float(va[i & 31]) + __uint_as_float(vb[i & 31]);
+    } else if (MODE == 5) {  // 16x128b.x16
+      ld_16x128b_x16(tb + col, va); ld_16x128b_x16(tb + col + (16u << 16), vb);
+      tmem_ld_wait32(va); tmem_ld_wait32(vb);
+      acc += __uint_as_float(va[i & 31]) + __uint_as_float(vb[i & 31]);
+    } else if (MODE == 6) {  // 8 x (32x32b.x8)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { ld_32x32b_x8(tb + col + 8 * c, va, 8 * c); ld_32x32b_x8(tb + col + 32 + 8 * c, vb, 8 * c); }
+      tmem_ld_wait32(va); tmem_ld_wait32(vb);
+      acc += __uint_as_float(va[i & 31]) + __uint_as_float(vb[i & 31]);
+    } else if (MODE == 7) {  // 16x256b + 64 ex2
+      ld_16x256b_x8(tb + col, va); ld_16x256b_x8(tb + col + (16u << 16), vb);
       tmem_ld_wait32(va); tmem_ld_wait32(vb);
 #pragma unroll
       for (int k = 0; k < 32; ++k) acc += fast_exp2(__uint_as_float(va[k]) * 1e-9f) + fast_exp2(__uint_as_float(vb[k]) * 1e-9f);
@@ -76,5 +127,9 @@ int main() {
   for (int c : {1, 2}) for (int w : {4, 8}) run<1>("ld pipelined", w, c);
   for (int c : {1, 2}) for (int w : {4, 8}) run<2>("ld + 64 ex2", w, c);
   for (int c : {1, 2}) for (int w : {4, 8}) run<3>("st x16 x2 + wait::st", w, c);
+  for (int c : {1, 2}) for (int w : {1, 4, 8}) run<4>("ld 16x256b.x8 x2 + wait", w, c);
+  for (int c : {1, 2}) for (int w : {4, 8}) run<5>("ld 16x128b.x16 x2 + wait", w, c);
+  for (int c : {1, 2}) for (int w : {4, 8}) run<6>("ld 32x32b.x8 x8 + wait", w, c);
+  for (int c : {1, 2}) for (int w : {4, 8}) run<7>("ld 16x256b + 64 ex2", w, c);
   return 0;
 }
