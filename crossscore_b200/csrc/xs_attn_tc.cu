@@ -32,6 +32,13 @@ namespace xs {
 constexpr int ATT_THREADS = 256;                        // warpgroup 0: softmax warps 0..3; warpgroup 1: TMA, MMA, 2 idle
 constexpr int ATT_BKV = 64;                             // keys per block
 constexpr int ATT_ST = 5;                               // K and V ring depth
+// Which of the 16 column pairs of a 32-column chunk take the polynomial exponential (FMA pipe) instead of MUFU.EX2.
+// Measured on the DINOv2 shape (I=48): none 0.235 ms, 3/16 0.229 ms, 7/16 0.235 ms, 8/16 0.241 ms, 10/16 0.250 ms --
+// the softmax warps are bound by their own instruction latency chain, not by the MUFU (62 % busy), so only a light
+// offload pays.
+#ifndef ATT_POLY_MASK
+#define ATT_POLY_MASK 0x0888
+#endif
 constexpr int ATT_REGS_SOFTMAX = 200;                   // setmaxnreg budgets (multiples of 8): 4*200 + 4*56 = 8*128
 constexpr int ATT_REGS_CTRL = 56;
 constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK runs ATT_NS blocks ahead of PV)
@@ -106,6 +113,8 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], float sl2, fl
     float2 a;
     if (DBG && (dbg & 8)) {  // timing experiment: no MUFU
       a = x;
+    } else if ((ATT_POLY_MASK >> i) & 1) {
+      a = exp2_poly2(x);  // FMA-pipe exponential: takes this pair off the MUFU
     } else {
       a.x = fast_exp2(x.x);
       a.y = fast_exp2(x.y);
@@ -171,15 +180,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* smK = smem + ATT_Q_BYTES;
   uint8_t* smV = smK + ATT_ST * ATT_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smV + ATT_ST * ATT_KV_BYTES);
-  uint64_t* q_full = bars + 0;                 // Q tile landed
-  uint64_t* q_empty = bars + 1;                // last QK^T of the tile complete: Q buffer free
-  uint64_t* kv_full = bars + 2;                // [ATT_ST] K_g and V_g landed
-  uint64_t* kv_empty = kv_full + ATT_ST;       // [ATT_ST] PV_g complete: slot free (also read by the O rescale)
-  uint64_t* s_full = kv_empty + ATT_ST;        // [ATT_NS]
-  uint64_t* p_full = s_full + ATT_NS;          // [ATT_NS]
-  uint64_t* o_full = p_full + ATT_NS;          // all PV of the tile complete
-  uint64_t* o_empty = o_full + 1;              // O read out by the softmax warps: next tile's PV_0 may overwrite
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  const SmemBar bar0{smem_u32(bars)};
+  const SmemBar q_full = bar0 + 0;             // Q tile landed
+  const SmemBar q_empty = bar0 + 1;            // last QK^T of the tile complete: Q buffer free
+  const SmemBar kv_full = bar0 + 2;            // [ATT_ST] K_g and V_g landed
+  const SmemBar kv_empty = kv_full + ATT_ST;   // [ATT_ST] PV_g complete: slot free (also read by the O rescale)
+  const SmemBar s_full = kv_empty + ATT_ST;    // [ATT_NS]
+  const SmemBar p_full = s_full + ATT_NS;      // [ATT_NS]
+  const SmemBar o_full = p_full + ATT_NS;      // all PV of the tile complete
+  const SmemBar o_empty = o_full + 1;          // O read out by the softmax warps: next tile's PV_0 may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * ATT_ST + 2 * ATT_NS + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,12 +201,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     for (int s = 0; s < ATT_ST; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(kv_full + (s), 1);
+      mbar_init(kv_empty + (s), 1);
     }
     for (int s = 0; s < ATT_NS; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4);  // one arrival per softmax warp
+      mbar_init(s_full + (s), 1);
+      mbar_init(p_full + (s), 4);  // one arrival per softmax warp
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, 4);
@@ -230,14 +240,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int j = 0; j < t.nkv; ++j, ++g) {
         const uint32_t s = g % ATT_ST;
         const int kv0 = t.kv_begin + j * ATT_BKV;
-        mbar_wait(&kv_empty[s], ((g / ATT_ST) & 1) ^ 1);
+        mbar_wait(kv_empty + (s), ((g / ATT_ST) & 1) ^ 1);
         if (elect_one_sync()) {
           if (DBG && (p.dbg & 64) && g >= ATT_ST) {  // timing experiment: no K/V traffic after the first ring fill
-            mbar_arrive(&kv_full[s]);
+            mbar_arrive(kv_full + (s));
           } else {
-            mbar_expect_tx(&kv_full[s], 2 * ATT_KV_BYTES);
-            tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, &kv_full[s], t.h * 64, kv0, b_kv);
-            tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, &kv_full[s], t.h * 64, kv0, b_kv);
+            mbar_expect_tx(kv_full + (s), 2 * ATT_KV_BYTES);
+            tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, kv_full + (s), t.h * 64, kv0, b_kv);
+            tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, kv_full + (s), t.h * 64, kv0, b_kv);
           }
         }
         __syncwarp();
@@ -253,14 +263,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t v_lo0 = umma_desc_lo(smem_u32(smV), 1024);
     auto issue_qk = [&](uint32_t gg, bool last_of_tile) {
       const uint32_t s = gg % ATT_ST;
-      mbar_wait(&kv_full[s], (gg / ATT_ST) & 1);  // K_gg (and V_gg) have landed
+      mbar_wait(kv_full + (s), (gg / ATT_ST) & 1);  // K_gg (and V_gg) have landed
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
         const uint32_t d_s = tb + (gg % ATT_NS) * 64;
+        if (!(DBG && (p.dbg & (256 | 2048)))) {  // (dbg 256: no MMAs at all, 2048: no QK^T MMAs)
 #pragma unroll
-        for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[gg % ATT_NS]);
+          for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        }
+        tc_commit(s_full + (gg % ATT_NS));
         if (last_of_tile) tc_commit(q_empty);  // Q buffer may be refilled once these MMAs have read it
       }
       __syncwarp();
@@ -281,7 +293,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t s = g % ATT_ST;
         const uint32_t sb = g % ATT_NS;
         // softmax has turned S_sb into P_g (and rescaled O if the row max moved)
-        mbar_wait(&p_full[sb], (g / ATT_NS) & 1);
+        mbar_wait(p_full + (sb), (g / ATT_NS) & 1);
         if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);  // previous tile's O has been read out
         pc.lap(1);  // waiting for P_g
         tc_fence_after();
@@ -292,14 +304,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < ATT_BKV / 16; ++k)
               umma_ss_lh<false>(tb + ATT_NS * 64, q_lo + 2 * k, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
-          } else {
+          } else if (!(DBG && (p.dbg & (256 | 1024)))) {  // (dbg 1024: no PV MMAs)
 #pragma unroll
             for (int k = 0; k < ATT_BKV / 16; ++k) {
               // A: 16 bf16 of P per row = 8 TMEM columns per K-step; B: 16 kv rows x 128 B = 2048 B per K-step
               umma_ts_lh(tb + ATT_NS * 64, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
             }
           }
-          tc_commit(&kv_empty[s]);  // K_g / V_g slot free; also the "PV_g complete" signal for the O rescale
+          tc_commit(kv_empty + (s));  // K_g / V_g slot free; also the "PV_g complete" signal for the O rescale
           if (j == nkv - 1) tc_commit(o_full);
         }
         __syncwarp();
@@ -335,7 +347,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // exponentials the tcgen05.ld of chunk B is in flight; while chunk B is in the exponentials, chunk A of
       // the NEXT block is in flight (S is triple-buffered, so S_{g+1} is normally complete long before).
       uint32_t va[32], vb[32];
-      if (lane == 0) mbar_wait(&s_full[g0 % ATT_NS], (g0 / ATT_NS) & 1);
+      if (lane == 0) mbar_wait(s_full + (g0 % ATT_NS), (g0 / ATT_NS) & 1);
       __syncwarp();
       tc_fence_after();
       tmem_ld32(tmem_base + lane_off + (g0 % ATT_NS) * 64, va);
@@ -355,7 +367,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (DBG && (p.dbg & 32)) {  // timing experiment: P "ready" before any softmax work (hand-off chain off the critical path)
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[sb]);
+          if (lane == 0) mbar_arrive(p_full + (sb));
         }
         if (!(DBG && (p.dbg & 4))) tmem_ld32(t_s + 32, vb);  // in flight during chunk A   (dbg 4: no S loads)
         pc.lap(1);
@@ -369,7 +381,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (j > 0 && !(DBG && (p.dbg & 2))) tmem_st16(t_s + 32, pka);  // (dbg 2: no P stores)
         if (j + 1 < nkv) {  // prefetch chunk A of the next block (va is dead until then)
           const uint32_t sn = (g + 1) % ATT_NS;
-          if (lane == 0) mbar_wait(&s_full[sn], ((g + 1) / ATT_NS) & 1);
+          if (lane == 0) mbar_wait(s_full + (sn), ((g + 1) / ATT_NS) & 1);
           __syncwarp();
           tc_fence_after();
           if (!(DBG && (p.dbg & 4))) tmem_ld32(tmem_base + lane_off + sn * 64, va);
@@ -405,7 +417,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (j > 0) {
             // O must hold PV of all earlier blocks of this tile: wait for the previous block's PV through its
             // K/V slot's kv_empty phase (the slot is refilled only ATT_ST blocks later: the parity cannot alias)
-            if (lane == 0) mbar_wait(&kv_empty[(g - 1) % ATT_ST], ((g - 1) / ATT_ST) & 1);
+            if (lane == 0) mbar_wait(kv_empty + ((g - 1) % ATT_ST), ((g - 1) / ATT_ST) & 1);
             __syncwarp();
             tc_fence_after();
 #pragma unroll
@@ -435,7 +447,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0 && !(DBG && (p.dbg & 32))) mbar_arrive(&p_full[sb]);
+        if (lane == 0 && !(DBG && (p.dbg & 32))) mbar_arrive(p_full + (sb));
         pc.lap(3);  // tcgen05.st of P + fences + arrive
       };
       for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});

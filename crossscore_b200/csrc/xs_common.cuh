@@ -103,6 +103,37 @@ __device__ __forceinline__ float2 fadd2(float2 x, float2 y) {
       : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y));
   return make_float2(__uint_as_float(static_cast<uint32_t>(d)), __uint_as_float(static_cast<uint32_t>(d >> 32)));
 }
+__device__ __forceinline__ float2 ffma2(float2 x, float2 y, float2 z) {  // x * y + z, elementwise
+  uint64_t d;
+  asm("{\n"
+      ".reg .b64 a, b, c;\n"
+      "mov.b64 a, {%1, %2};\n"
+      "mov.b64 b, {%3, %4};\n"
+      "mov.b64 c, {%5, %6};\n"
+      "fma.rn.f32x2 %0, a, b, c;\n"
+      "}\n"
+      : "=l"(d)
+      : "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y), "f"(z.x), "f"(z.y));
+  return make_float2(__uint_as_float(static_cast<uint32_t>(d)), __uint_as_float(static_cast<uint32_t>(d >> 32)));
+}
+// 2^x for a pair of fp32 values on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r with the
+// 1.5 * 2^23 magic constant, cubic minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, far below
+// the bf16 rounding of the softmax numerators it feeds), exponent inserted by an integer shift-add.
+// Inputs are clamped at -126 (result flushes towards 0); inputs up to +127 are exact in range.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = fadd2(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 nf = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = ffma2(nf, make_float2(-1.0f, -1.0f), x);
+  float2 p = ffma2(make_float2(0.055171460f, 0.055171460f), r, make_float2(0.24261086f, 0.24261086f));
+  p = ffma2(p, r, make_float2(0.69326097f, 0.69326097f));
+  p = ffma2(p, r, make_float2(0.99992812f, 0.99992812f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  y.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return y;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -133,20 +164,34 @@ __device__ __forceinline__ float apply_act(float v) {
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// A barrier named by its 32-bit shared-window address (kernels whose hot loops wait on many barriers keep one
+// base register instead of re-deriving shared addresses from generic pointers at every use).
+struct SmemBar {
+  uint32_t addr;
+  __device__ __forceinline__ SmemBar operator+(int i) const { return SmemBar{addr + 8u * static_cast<uint32_t>(i)}; }
+  __device__ __forceinline__ SmemBar operator+(uint32_t i) const { return SmemBar{addr + 8u * i}; }
+};
+__device__ __forceinline__ uint32_t bar_u32(const uint64_t* bar) { return smem_u32(bar); }
+__device__ __forceinline__ uint32_t bar_u32(SmemBar bar) { return bar.addr; }
+
+template <class B>
+__device__ __forceinline__ void mbar_init(B bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+template <class B>
+__device__ __forceinline__ void mbar_expect_tx(B bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+template <class B>
+__device__ __forceinline__ void mbar_arrive(B bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+template <class B>
+__device__ __forceinline__ bool mbar_try_wait(B bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -155,7 +200,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -165,7 +210,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef XS_MBAR_HINT_NS
 #define XS_MBAR_HINT_NS 20000
 #endif
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+template <class B>
+__device__ __forceinline__ bool mbar_try_wait_hint(B bar, uint32_t parity) {
 #if XS_MBAR_HINT_NS == 0
   return mbar_try_wait(bar, parity);  // default (implementation-defined, short) suspend
 #else
@@ -177,14 +223,15 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)XS_MBAR_HINT_NS)
+      : "r"(bar_u32(bar)), "r"(parity), "r"((uint32_t)XS_MBAR_HINT_NS)
       : "memory");
   return ok != 0;
 #endif
 }
 // Fully inline (no calls: a call inside a setmaxnreg-raised region would pin that region to the kernel-wide
 // register cap).  A pipeline bug traps after a few seconds instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+template <class B>
+__device__ __forceinline__ void mbar_wait(B bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
 #pragma unroll 1
@@ -202,17 +249,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+template <class B>
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, B bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+template <class B>
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, B bar, int c0, int c1,
                                             int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
@@ -267,8 +316,9 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // mbarrier arrive when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+template <class B>
+__device__ __forceinline__ void tc_commit(B bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u32(bar))
                : "memory");
 }
 
@@ -412,8 +462,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // possibly remote barrier
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a (possibly remote) barrier of the cluster.  RELAXED: the callers order their tcgen05 / TMEM accesses
+// with tcgen05.wait + tcgen05.fence::before_thread_sync and publish no generic-proxy data through this barrier; a
+// release at cluster scope costs a MEMBAR + ERRBAR per arrive (30 % of the epilogue warps' time, measured).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {  // same warp id in both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
@@ -440,7 +493,7 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
       ".reg .b16 m;\n"
       "mov.b16 m, 3;\n"
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
-      "}\n" ::"r"(smem_u32(bar))
+      "}\n" ::"r"(bar_u32(bar))
       : "memory");
 }
 // D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; issued by the leader CTA only

@@ -29,8 +29,8 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_THREADS = 256;
 constexpr int ACC_STAGE_COLS = 256;  // TMEM column offset between the two accumulator stages
+constexpr int GEMM_KB_MAX = 6;       // A-stationary mode: K <= 6 * 64
 constexpr int JIG_LD = 197;          // padded row length of the fp32 score staging tile
-constexpr uint32_t EPI_WARP_STAGE_BYTES = 32 * 128;  // one 32-row staging tile of an epilogue warp (128-byte rows max)
 
 enum Epi : int { EPI_STORE = 0, EPI_JIGSAW = 1 };
 enum InT : int { IN_BF16 = 0, IN_TF32 = 1 };
@@ -46,16 +46,19 @@ struct JigsawParams {
   float power;
 };
 
-template <int BN, int STAGES, int EPI, int CTA2 = 0>
+template <int BN, int STAGES, int EPI, int CTA2 = 0, int OUT = 0>
 struct GemmSmem {
+  // one 32-row x 32-column staging tile of an epilogue warp (64-byte rows for bf16 output, 128-byte rows for fp32)
+  static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * (OUT == 1 ? 4 : 2);
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * GEMM_BK * 2;  // a CTA pair splits the W tile rows
-  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * EPI_WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4;
+  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4;
+  static constexpr int A_SLOTS = (CTA2 == 2) ? GEMM_KB_MAX : STAGES;  // A-stationary: one slot per k-block of the m-block
   static constexpr uint32_t OFF_A = 0;
-  static constexpr uint32_t OFF_B = OFF_A + STAGES * A_BYTES;
+  static constexpr uint32_t OFF_B = OFF_A + A_SLOTS * A_BYTES;
   static constexpr uint32_t OFF_STAGING = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_BAR = (OFF_STAGING + STAGING_BYTES + 15u) & ~15u;
-  static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4 + 2 * GEMM_KB_MAX) * 8 + 16;
   static constexpr uint32_t TOTAL = OFF_BAR + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment of the base
 };
 
@@ -64,12 +67,16 @@ struct GemmSmem {
 // holds its 128 accumulator rows in ITS TMEM; the leader CTA (rank 0) issues the MMAs, whose completion is
 // multicast to both CTAs' barriers.  Shared-memory fill traffic per output element falls by a third, which is
 // what bounds these K = 384 GEMMs (L2 -> SM bandwidth), see DESIGN.md.
+// CTA2 = 2: CTA pairs with a STATIONARY A block (K <= 384).  A pair owns 256 rows of A at a time: its six k-blocks
+// stay in shared memory while the pair walks ALL n-tiles of that row block, so only W (half a tile per CTA) is
+// streamed.  Per 128 x BN output tile a CTA then pulls BN/2 x 384 x 2 bytes from L2 (74 KB at BN = 192) instead
+// of 240 KB, which moves the K = 384 GEMMs from the L2 -> SM bandwidth bound to the MMA / epilogue bound.
 template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
                JigsawParams jp) {
-  using L = GemmSmem<BN, STAGES, EPI, CTA2>;
+  using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT>;
   static_assert(!CTA2 || (IN == IN_BF16 && EPI == EPI_STORE), "CTA pairs: bf16 store epilogue only");
   constexpr int NC = CTA2 ? 2 : 1;                       // CTAs per tile
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader
@@ -85,7 +92,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;            // [GEMM_KB_MAX] A-stationary mode only
+  uint64_t* a_empty = a_full + GEMM_KB_MAX;     // [GEMM_KB_MAX]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + GEMM_KB_MAX);
+  constexpr bool ASTAT = CTA2 == 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,6 +105,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int BKE = (IN == IN_TF32) ? 32 : 64;  // elements per 128-byte smem row
   const int num_k = (K + BKE - 1) / BKE;
   const int num_tiles = num_m * num_n;
+  // tile sequence of this worker: streaming modes walk tiles worker, worker + n_workers, ... (n fastest);
+  // the A-stationary mode walks row blocks worker, worker + n_workers, ... and all n-tiles inside each
+  const int my_rounds = worker < num_m ? (num_m - worker + n_workers - 1) / n_workers : 0;
+  const int my_count = ASTAT ? my_rounds * num_n : (worker < num_tiles ? (num_tiles - worker + n_workers - 1) / n_workers : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -107,6 +121,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 8 * NC);  // one elected lane per epilogue warp (of both CTAs of a pair)
+    }
+    for (int s = 0; s < GEMM_KB_MAX; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
     }
     fence_mbar_init();
   }
@@ -123,6 +141,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     uint32_t stage = 0, phase = 0;
+    if constexpr (ASTAT) {
+      for (int r = 0; r < my_rounds; ++r) {
+        const int m_blk = worker + r * n_workers;
+        for (int n_blk = 0; n_blk < num_n; ++n_blk) {
+          for (int kb = 0; kb < num_k; ++kb) {
+            if (n_blk == 0) {
+              // slot kb was last read by the previous row block's last n-tile; A and the first W tile are issued
+              // k-block by k-block so neither waits behind the other
+              mbar_wait(&a_empty[kb], (r & 1) ^ 1);
+              if (elect_one_sync()) {
+                const uint32_t a_leader = map_to_cta(smem_u32(&a_full[kb]), 0);
+                if (rank == 0) mbar_expect_tx(&a_full[kb], 2 * L::A_BYTES);
+                tma_load_2d_pair(smA + kb * L::A_BYTES, &tmA, a_leader, kb * BKE,
+                                 (m_blk * 2 + static_cast<int>(rank)) * GEMM_BM);
+              }
+              __syncwarp();
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one_sync()) {
+              const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::B_BYTES);
+              tma_load_2d_pair(smB + stage * L::B_BYTES, &tmW, full_leader, kb * BKE,
+                               n_blk * BN + static_cast<int>(rank) * (BN / 2));
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else
     for (int tile = worker; tile < num_tiles; tile += n_workers) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       for (int kb = 0; kb < num_k; ++kb) {
@@ -154,6 +202,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA), 16);
     const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB), 16);
     uint32_t stage = 0, phase = 0, acc_stage = 0, acc_phase = 0;
+    if constexpr (ASTAT) {
+      for (int r = 0; r < my_rounds; ++r) {
+        for (int n_blk = 0; n_blk < num_n; ++n_blk) {
+          mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tb + acc_stage * ACC_STAGE_COLS;
+          for (int kb = 0; kb < num_k; ++kb) {
+            if (n_blk == 0) mbar_wait(&a_full[kb], r & 1);  // this row block's k-block kb has landed in both CTAs
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint32_t a_lo = a_lo0 + kb * (L::A_BYTES >> 4);
+              const uint32_t b_lo = b_lo0 + stage * (L::B_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ss_lh_pair(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              tc_commit_pair(&empty_bar[stage]);
+              if (n_blk == num_n - 1) tc_commit_pair(&a_empty[kb]);  // last reader of A slot kb in this row block
+              if (kb == num_k - 1) tc_commit_pair(&tmem_full[acc_stage]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          acc_stage ^= 1;
+          if (acc_stage == 0) acc_phase ^= 1;
+        }
+      }
+    } else
     for (int tile = worker; tile < num_tiles; tile += n_workers) {
       mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
       tc_fence_after();
@@ -192,8 +268,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;          // row of the tile owned by this thread
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t chunk_counter = 0;
-    for (int tile = worker; tile < num_tiles; tile += n_workers) {
-      const int m_blk = (tile / num_n) * NC + static_cast<int>(rank), n_blk = tile % num_n;
+    for (int i = 0; i < my_count; ++i) {
+      int m_tile, n_blk;  // (pair) row block and n-tile of this worker's i-th tile
+      if constexpr (ASTAT) {
+        m_tile = worker + (i / num_n) * n_workers;
+        n_blk = i % num_n;
+      } else {
+        const int tile = worker + i * n_workers;
+        m_tile = tile / num_n;
+        n_blk = tile % num_n;
+      }
+      const int m_blk = m_tile * NC + static_cast<int>(rank);
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc_stage * ACC_STAGE_COLS + (static_cast<uint32_t>(q * 32) << 16);
@@ -205,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NSTEP = BN / 32;
         constexpr int MY_STEPS = NSTEP / 2;
         static_assert(NSTEP % 2 == 0, "BN must be a multiple of 64");
-        uint8_t* my_staging = staging + (warp - 4) * (2 * EPI_WARP_STAGE_BYTES);
+        uint8_t* my_staging = staging + (warp - 4) * (2 * L::WARP_STAGE_BYTES);
         const int m0 = m_blk * GEMM_BM + q * 32;
         uint32_t v[2][32];
         tmem_ld32(taddr0 + half * 32, v[0]);
@@ -229,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           const int n0 = n_blk * BN + c * 32;
-          uint8_t* srow = my_staging + buf * EPI_WARP_STAGE_BYTES;
+          uint8_t* srow = my_staging + buf * L::WARP_STAGE_BYTES;
           const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
           const uint32_t(&vv)[32] = v[i & 1];
           if constexpr (OUT == OUT_BF16) {
@@ -343,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2 = 0>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                        int N, int K, JigsawParams jp, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES, EPI, CTA2>;
+  using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT>;
   constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
   constexpr int OUT_B = (OUT == OUT_F32) ? 4 : 2;
   constexpr uint32_t BKE = 128 / IN_B;
@@ -374,8 +459,9 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
   auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT, IN, OUT, CTA2>;
   XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
   if constexpr (CTA2) {
-    const int num_tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * (N / BN);
-    const int pairs = num_tiles < num_sms() / 2 ? num_tiles : num_sms() / 2;
+    const int num_m2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int units = CTA2 == 2 ? num_m2 : num_m2 * (N / BN);  // A-stationary pairs walk whole row blocks
+    const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -432,21 +518,28 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
   if (!in_tf32 && !out_f32) {
     // CTA pairs for the long-K GEMM (fc2, K = 1536: 1.35 PF vs 1.13 PF single-CTA, measured); the K = 384 GEMMs
     // are bound by their epilogue / operand refill per tile and run faster as independent CTAs.
-    // XS_GEMM_PAIR=0 / 2 forces the single-CTA / pair kernel.
+    // XS_GEMM_PAIR=0 / 2 forces the single-CTA / streaming-pair kernel (3: no A-stationary mode).
     static int pair_mode = -1;
     if (pair_mode < 0) {
       const char* e = getenv("XS_GEMM_PAIR");
       pair_mode = e ? atoi(e) : 1;
     }
     const int bn = use192 ? 192 : 256;
-    const bool fits = ((M + 255) / 256) * (N / bn) >= num_sms() / 2;
-    const bool pair = fits && (pair_mode == 2 || (pair_mode == 1 && K >= 1024));
+    const int num_m2 = (M + 255) / 256;
+    const bool fits = num_m2 * (N / bn) >= num_sms() / 2;
+    const bool pair = fits && (pair_mode == 2 || ((pair_mode == 1 || pair_mode == 3) && K >= 1024));
+    // K <= 384 (qkv, proj, fc1): A-stationary pairs once every pair of SMs has a 256-row block of its own
+    const bool astat = pair_mode == 1 && K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2;
+    if (astat) {
+      if (use192) return dispatch_act<192, 8, IN_BF16, OUT_BF16, 2>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+      return dispatch_act<256, 6, IN_BF16, OUT_BF16, 2>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+    }
     if (pair) {
-      if (use192) return dispatch_act<192, 5, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
-      return dispatch_act<256, 5, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+      if (use192) return dispatch_act<192, 6, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+      return dispatch_act<256, 6, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
     }
     if (use192) return dispatch_act<192, 4, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
-    return dispatch_act<256, 3, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
+    return dispatch_act<256, 4, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
   }
   JigsawParams jp{};
   if (!in_tf32 && out_f32) {  // bf16 operands, fp32 result (residual deltas kept unrounded)

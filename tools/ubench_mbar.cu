@@ -19,7 +19,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 template <int MODE>
 __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, int lane) {
-  if (MODE == 0 || MODE == 4 || MODE == 5) { while (!mbar_try_wait(bar, parity)) {} }
+  if (MODE == 0 || MODE == 4 || MODE == 5 || MODE == 6) { while (!mbar_try_wait(bar, parity)) {} }
   else if (MODE == 1) { while (!mbar_try_wait_hint(bar, parity)) {} }
   else if (MODE == 2) { while (!mbar_test_wait(bar, parity)) {} }
   else { if (lane == 0) { while (!mbar_test_wait(bar, parity)) {} } __syncwarp(); }
@@ -27,22 +27,23 @@ __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, int lane) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k(int iters, long long* out, float* sink) {
-  __shared__ __align__(1024) uint8_t tile[4096];
+  __shared__ __align__(1024) uint8_t tile[16384 + 2048];
   __shared__ uint64_t bars[2];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) { mbar_init(&bars[0], MODE == 5 ? 1 : 32); mbar_init(&bars[1], 32); fence_mbar_init(); }
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(tile)[i] = 0;
-  if (MODE == 5 && warp == 0) tmem_alloc(&slot, 32);
+  if (threadIdx.x == 0) { mbar_init(&bars[0], MODE >= 5 ? 1 : 32); mbar_init(&bars[1], 32); fence_mbar_init(); }
+  for (int i = threadIdx.x; i < (16384 + 2048) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tile)[i] = 0;
+  if (MODE >= 5 && warp == 0) tmem_alloc(&slot, 32);
   fence_proxy_async_smem();
   tc_fence_before(); __syncthreads(); tc_fence_after();
   float acc = threadIdx.x;
   if (warp == 0) {
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
-      if (MODE == 5) {
+      if (MODE >= 5) {
         if (elect_one_sync()) {
-          umma_ss_lh<false>(slot, umma_desc_lo(smem_u32(tile), 16), umma_desc_lo(smem_u32(tile), 16), umma_idesc_bf16(128, 16, 0, 0), 0);
+          if (MODE == 5)
+            umma_ss_lh<false>(slot, umma_desc_lo(smem_u32(tile), 16), umma_desc_lo(smem_u32(tile + 16384), 16), umma_idesc_bf16(128, 16, 0, 0), 0);
           tc_commit(&bars[0]);
         }
         __syncwarp();
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k(int iters, long long* out, float* sink)
   } else if (warp == 1) {
     for (int i = 0; i < iters; ++i) {
       wait<MODE>(&bars[0], i & 1, lane);
-      if (MODE == 5) tc_fence_after();
+      if (MODE >= 5) tc_fence_after();
       mbar_arrive(&bars[1]);
     }
   } else if (MODE == 4) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) k(int iters, long long* out, float* sink)
   }
   if (acc == 12345.678f) sink[0] = acc;
   tc_fence_before(); __syncthreads();
-  if (MODE == 5 && warp == 0) { tc_fence_after(); tmem_dealloc(slot, 32); }
+  if (MODE >= 5 && warp == 0) { tc_fence_after(); tmem_dealloc(slot, 32); }
 }
 
 template <int MODE>
@@ -85,6 +86,7 @@ int main() {
   run<2>("test_wait spin (all lanes)", 64);
   run<3>("test_wait spin (lane 0) + syncwarp", 64);
   run<4>("try_wait loop, 6 busy FFMA warps", 256);
-  run<5>("tcgen05.commit -> try_wait -> arrive -> try_wait", 64);
+  run<5>("1 MMA + tcgen05.commit -> try_wait -> arrive -> try_wait", 64);
+  run<6>("tcgen05.commit (no MMA) -> try_wait -> arrive -> try_wait", 64);
   return 0;
 }
