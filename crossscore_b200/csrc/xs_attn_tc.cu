@@ -342,6 +342,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       float m = -INFINITY;  // reference max of the row (log2 domain); may be stale (see below)
       float l = 0.f;        // running sum of exp2(s - m)
+      // P_g's hand-over (wait for the tcgen05.st, fence, arrive on p_full) is deferred into the next block, behind
+      // the first chunk's exponentials, so the store latency is never waited for
+      int pending_sb = -1;
+      auto flush_pending = [&]() {
+        if (pending_sb >= 0) {
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full + pending_sb);
+          pending_sb = -1;
+        }
+      };
 
       // Software pipeline: a block is processed as two 32-column chunks (va, vb).  While chunk A is in the
       // exponentials the tcgen05.ld of chunk B is in flight; while chunk B is in the exponentials, chunk A of
@@ -364,15 +376,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float neg_m = -m;
 
         tmem_ld_wait32(va);
-        if (DBG && (p.dbg & 32)) {  // timing experiment: P "ready" before any softmax work (hand-off chain off the critical path)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(p_full + (sb));
-        }
         if (!(DBG && (p.dbg & 4))) tmem_ld32(t_s + 32, vb);  // in flight during chunk A   (dbg 4: no S loads)
         pc.lap(1);
         if constexpr (MASK) mask_tail(va, valid);
         if (j > 0) exp_chunk<DBG>(va, sl2, neg_m, pka, acc0, acc1, p.dbg);
+        flush_pending();  // previous block's P
         pc.lap(2);
         tmem_ld_wait32(vb);
         pc.lap(6);  // residual wait for chunk B
@@ -444,14 +452,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         l += bsum;
         pc.lap(2);  // exp2 / pack
         if (!(DBG && (p.dbg & 2))) tmem_st16(t_s + 48, pkb);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0 && !(DBG && (p.dbg & 32))) mbar_arrive(p_full + (sb));
-        pc.lap(3);  // tcgen05.st of P + fences + arrive
+        pending_sb = static_cast<int>(sb);
+        pc.lap(3);  // tcgen05.st of P issued
       };
       for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
       block(nkv - 1, MaskYes{});
+      flush_pending();
       g0 += nkv;
 
       // ---- epilogue: read O out of TMEM (frees it for the next tile's PV_0), then O / l and log-sum-exp ----

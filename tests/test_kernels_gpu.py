@@ -69,7 +69,11 @@ def test_gemm_f32(M, N, K, act):
     (777, 384, 1536, ACT_NONE),     # fc2 K
     (1369, 2048, 384, ACT_NONE),    # BN=256
     (1369, 512, 384, ACT_RELU),
-    (40000, 384, 384, ACT_LEAKY),   # many tiles per CTA (persistent loop, phase wrap)
+    (40000, 384, 384, ACT_LEAKY),   # many tiles per CTA (persistent loop, phase wrap); A-stationary CTA pairs, BN=192
+    (19999, 1152, 384, ACT_NONE),   # A-stationary CTA pairs, 6 n-tiles per row block, ragged M (peer CTA rows out of range)
+    (20000, 1536, 384, ACT_GELU),   # A-stationary CTA pairs, BN=256
+    (19999, 384, 1536, ACT_NONE),   # streaming CTA pairs (cta_group::2), long K
+    (18945, 512, 1024, ACT_RELU),   # streaming CTA pairs, BN=256
 ])
 def test_gemm_bf16_tc(M, N, K, act):
     A = rnd(M, K, seed=1, dtype=torch.bfloat16)
