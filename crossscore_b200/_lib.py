@@ -30,6 +30,7 @@ SIGNATURES = {
     "xs_pe_resample_bilinear_ac": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "xs_pos_embed_resample_bicubic": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "xs_gemm_bias_act": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "xs_gemm_bias_residual": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_lse_merge": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _i, _p]),
     "xs_head_score_jigsaw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),

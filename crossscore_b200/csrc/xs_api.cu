@@ -194,6 +194,13 @@ int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float
   return -1;
 }
 
+int xs_gemm_bias_residual(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh, int M,
+                          int N, int K, int dtype, xs_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XS_CHECK_ARG(dtype == XS_BF16, "gemm_bias_residual: bf16 operands only (the fp32 parity mode adds in xs_layernorm)");
+  return gemm_tc(A, lda, W, ldw, bias, h, ldh, M, N, K, ACT_NONE, 0, 2, st);
+}
+
 int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk,
                   int head_dim, int head_slot, long long q_row_stride, long long q_batch_stride,
                   long long kv_row_stride, long long kv_batch_stride, int kv_shared, int nsplit, int o_is_f32,

@@ -34,7 +34,7 @@ constexpr int JIG_LD = 197;          // padded row length of the fp32 score stag
 
 enum Epi : int { EPI_STORE = 0, EPI_JIGSAW = 1 };
 enum InT : int { IN_BF16 = 0, IN_TF32 = 1 };
-enum OutT : int { OUT_BF16 = 0, OUT_F32 = 1 };
+enum OutT : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ADD = 2 };  // ADD: out += tile (TMA reduce-store, fp32)
 
 struct JigsawParams {
   float* score;  // (B, 14*ph, 14*pw) fp32
@@ -49,7 +49,7 @@ struct JigsawParams {
 template <int BN, int STAGES, int EPI, int CTA2 = 0, int OUT = 0>
 struct GemmSmem {
   // one 32-row x 32-column staging tile of an epilogue warp (64-byte rows for bf16 output, 128-byte rows for fp32)
-  static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * (OUT == 1 ? 4 : 2);
+  static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * (OUT != 0 ? 4 : 2);
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * GEMM_BK * 2;  // a CTA pair splits the W tile rows
   static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4;
@@ -352,7 +352,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, srow, n0, m0);  // box = 32 columns x 32 rows; clips the M tail
+            // box = 32 columns x 32 rows; clips the M tail
+            if constexpr (OUT == OUT_F32_ADD) tma_reduce_add_2d(&tmC, srow, n0, m0);  // residual stream += tile
+            else tma_store_2d(&tmC, srow, n0, m0);
             tma_store_commit();
           }
         }
@@ -430,7 +432,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
                        int N, int K, JigsawParams jp, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT>;
   constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
-  constexpr int OUT_B = (OUT == OUT_F32) ? 4 : 2;
+  constexpr int OUT_B = (OUT != OUT_BF16) ? 4 : 2;
   constexpr uint32_t BKE = 128 / IN_B;
   CUtensorMap tmA, tmW, tmC;
   {
@@ -501,6 +503,7 @@ static int dispatch_act(const void* A, int lda, const void* W, int ldw, const fl
 }
 
 // Tensor-core GEMM entry used by xs_api.cu.  in_tf32: A/W are fp32 (TF32 multiply), else bf16.
+// out_f32: 0 bf16 output, 1 fp32 output, 2 fp32 output accumulated in place (out += ...).
 // N must be a multiple of 192 or 256; row pitches must be multiples of 16 bytes.
 int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
             int act, int in_tf32, int out_f32, cudaStream_t stream) {
@@ -542,6 +545,26 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
     return dispatch_act<256, 4, IN_BF16, OUT_BF16>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
   }
   JigsawParams jp{};
+  if (!in_tf32 && out_f32 == 2) {
+    // bf16 operands, out (fp32) += A W^T + bias: the residual add of the DINOv2 blocks (attention.output.dense and
+    // mlp.fc2 with LayerScale folded in, modeling_dinov2.py:367-386) done by the TMA reduce-store of the epilogue,
+    // so the delta never exists in HBM and the LayerNorm that follows reads the residual stream only
+    XS_CHECK_ARG(act == ACT_NONE, "gemm: residual accumulate supports act=NONE only");
+    XS_CHECK_ARG(use192, "gemm: residual accumulate needs N %% 192 == 0 (N=%d)", N);
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+      const char* e = getenv("XS_GEMM_PAIR");
+      pair_mode = e ? atoi(e) : 1;
+    }
+    const int num_m2 = (M + 255) / 256;
+    const bool fits = num_m2 * (N / 192) >= num_sms() / 2;
+    if (pair_mode == 1 && K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
+      return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 2>(XS_GEMM_ARGS);
+    if (pair_mode != 0 && fits && K >= 1024)
+      return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 1>(XS_GEMM_ARGS);
+    return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD>(XS_GEMM_ARGS);
+  }
+  XS_CHECK_ARG(out_f32 != 2, "gemm: residual accumulate needs bf16 operands");
   if (!in_tf32 && out_f32) {  // bf16 operands, fp32 result (residual deltas kept unrounded)
     XS_CHECK_ARG(act == ACT_NONE, "gemm: bf16->fp32 supports act=NONE only");
     if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32>(XS_GEMM_ARGS);

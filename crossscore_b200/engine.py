@@ -18,6 +18,7 @@ Data layout in HBM (C = 384, P = patches/image, T = P + 1, I = images in the bat
 from __future__ import annotations
 
 import math
+import os
 from contextlib import contextmanager
 from typing import Dict, Optional
 
@@ -169,6 +170,9 @@ class Engine:
         self.do_self_attn, self.do_short_cut = do_self_attn, do_short_cut
         self.use_tanh, self.power = bool(use_tanh), float(power)
         self._ws = {}
+        # bf16 mode: residual adds of the DINOv2 blocks happen in the GEMM epilogue (XS_FUSE_RESIDUAL=0: separate
+        # bf16 delta + add inside the LayerNorm kernel, the pre-fusion plan, kept for A/B measurements)
+        self.fuse_residual = os.environ.get("XS_FUSE_RESIDUAL", "1") != "0"
         self.prof = None  # list of (tag, algorithmic flops, algorithmic bytes, start event, stop event) when profiling
 
     @contextmanager
@@ -213,6 +217,15 @@ class Engine:
         with self._op(tag, flops):
             call("xs_gemm_bias_act", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(out),
                  out.stride(0), M, N, K, act, dt, odt, st)
+
+    def _gemm_residual(self, A, Wt, bias, h, st, tag="gemm"):
+        """h (fp32, in place) += A @ Wt^T + bias: residual add fused into the GEMM epilogue (bf16 mode)."""
+        M, K = A.shape
+        N = Wt.shape[0]
+        assert A.dtype == torch.bfloat16 and Wt.dtype == torch.bfloat16 and h.dtype == torch.float32
+        with self._op(tag, 2.0 * M * N * K):
+            call("xs_gemm_bias_residual", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(h),
+                 h.stride(0), M, N, K, DT_BF16, st)
 
     def _ln(self, res_in, delta, res_out, g, b, eps, y, y32, rows, st):
         dt = DT_BF16 if (delta is not None and delta.dtype == torch.bfloat16) or \
@@ -282,10 +295,22 @@ class Engine:
         with self._op("embed_ln", 0.0, R * C * (4 + 4 + y.element_size())):
             call("xs_embed_cls_pos_ln", _ptr(tok), DT_F32, _ptr(w.cls), _ptr(pos), _ptr(h), _ptr(L0["ln1_g"]),
                  _ptr(L0["ln1_b"]), DINO_EPS, _ptr(y), I, P, self.dt, st)
+        fused = self.dt == DT_BF16 and self.fuse_residual
         for l, L in enumerate(w.layers):
             self._gemm(y, L["wqkv"], L["bqkv"], qkv, ACT_NONE, st, tag="gemm_dino_qkv")
             self._attn(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, I, DINO_HEADS, T, T, 64, 64,
                        3 * C, T * 3 * C, 3 * C, T * 3 * C, False, st, name="dino")
+            if fused:
+                # the GEMM epilogue adds its tile into the fp32 residual stream (TMA reduce-store); the LayerNorm
+                # that follows only reads h
+                self._gemm_residual(att, L["wo"], L["bo"], h, st, tag="gemm_dino_proj")
+                self._ln(h, None, None, L["ln2_g"], L["ln2_b"], DINO_EPS, y, None, R, st)  # y = LN2(h)
+                self._gemm(y, L["w1"], L["b1"], g1, ACT_GELU, st, tag="gemm_dino_fc1")
+                self._gemm_residual(g1, L["w2"], L["b2"], h, st, tag="gemm_dino_fc2")
+                if l + 1 < DINO_LAYERS:
+                    Ln = w.layers[l + 1]
+                    self._ln(h, None, None, Ln["ln1_g"], Ln["ln1_b"], DINO_EPS, y, None, R, st)  # y = LN1_{l+1}(h)
+                continue
             self._gemm(att, L["wo"], L["bo"], d, ACT_NONE, st, tag="gemm_dino_proj")
             self._ln(h, d, h, L["ln2_g"], L["ln2_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN2(h)
             self._gemm(y, L["w1"], L["b1"], g1, ACT_GELU, st, tag="gemm_dino_fc1")
@@ -293,7 +318,7 @@ class Engine:
             if l + 1 < DINO_LAYERS:
                 Ln = w.layers[l + 1]
                 self._ln(h, d, h, Ln["ln1_g"], Ln["ln1_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN1_{l+1}(h)
-        return h, d, I, P
+        return h, (None if fused else d), I, P
 
     def features(self, query_img, ref_imgs, st, want_mem=True):
         """DINOv2 + final LN + CLS drop + PE.  query_img (B,3,H,W) or None, ref_imgs (B,N,3,H,W) or None.
@@ -314,7 +339,8 @@ class Engine:
         _, pe = w.tables(ph, pw, st)
         xq32 = self._buf("xq32", (nq * P, C), torch.float32) if nq else None
         mem = self._buf("mem", (nr * P, C), self.adtype) if nr and want_mem else None
-        with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + 2 * d.element_size())):
+        es = self.adtype.itemsize
+        with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + (es if d is not None else 0) + es)):
             call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS, _ptr(pe),
                  _ptr(xq32), None, _ptr(mem), I, nq, P, self.dt, st)
         return xq32, mem

@@ -99,6 +99,14 @@ int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw
 int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc,
                      int M, int N, int K, int act, int dtype, int out_dtype, xs_stream_t stream);
 
+/* K5,K7  h[M,N] += A[M,K] @ W[N,K]^T + bias[N]   (fp32 residual stream updated in place)
+ *     Dinov2Layer's `layer_scale(attention_output) + hidden_states` and `layer_scale2(mlp(...)) + hidden_states`
+ *     ($SP/transformers/models/dinov2/modeling_dinov2.py:367-386) with LayerScale folded into W / bias: the add is
+ *     performed by the epilogue's TMA reduce-store, so the delta never round-trips through HBM (nor through bf16).
+ *     dtype = XS_DTYPE_BF16 only; N multiple of 192; every element of h receives exactly one add (deterministic). */
+int xs_gemm_bias_residual(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
+                          int M, int N, int K, int dtype, xs_stream_t stream);
+
 /* K4,K9,K10  O = softmax(Q K^T * scale) V  per (batch, head), no mask
  *     (modeling_dinov2.py:203-234; $SP/torch/nn/functional.py:6630-6692 via transformer.py:182-205).
  *     head_slot: column pitch between heads in q/k/v rows (bf16: must be 64).  kv_shared: all batches

@@ -126,6 +126,33 @@ def test_gemm_bf16_in_f32_out():
     assert (out.double() - ref).abs().max() < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [
+    (128, 384, 384),      # single CTA per tile
+    (1000, 384, 1536),    # single CTA, long K, ragged M
+    (40001, 384, 384),    # A-stationary CTA pairs (proj), ragged M: the reduce-store clips the tail rows
+    (39999, 384, 1536),   # streaming CTA pairs (fc2)
+])
+def test_gemm_bias_residual(M, N, K):
+    """h += A W^T + b in place (TMA reduce-store epilogue): every element gets exactly one fp32 add."""
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+    b = rnd(N, seed=3)
+    h0 = rnd(M + 3, N, seed=4, scale=3.0)  # 3 guard rows behind the tail
+    h = h0.clone()
+    call("xs_gemm_bias_residual", P(A), K, P(W), K, P(b), P(h), N, M, N, K, DT_BF16, st())
+    torch.cuda.synchronize()
+    ref = h0[:M].double() + A.double() @ W.double().T + b.double()
+    assert (h[:M].double() - ref).abs().max() < 2e-3
+    assert torch.equal(h[M:], h0[M:])
+    # twice more: accumulates, deterministic
+    h2 = h0.clone()
+    call("xs_gemm_bias_residual", P(A), K, P(W), K, P(b), P(h2), N, M, N, K, DT_BF16, st())
+    torch.cuda.synchronize()
+    assert torch.equal(h2, h)
+    with pytest.raises(_lib.XsError):
+        call("xs_gemm_bias_residual", P(A), K, P(W), K, P(b), P(h), N, M, N, K, DT_F32, st())
+
+
 def test_gemm_bf16_rejects_bad_shapes():
     A = rnd(128, 384, dtype=torch.bfloat16)
     W = rnd(200, 384, dtype=torch.bfloat16)

@@ -42,6 +42,20 @@ __device__ __forceinline__ void ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[32], 
                : "memory");
 }
 
+// 32x32b.x32 with .pack::16b: 64 TMEM columns (low 16 bits of each) -> 32 registers
+__device__ __forceinline__ void ld_32x32b_x32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512) ubench(int iters, long long* out, int tmem_cols, float* sink) {
   __shared__ uint32_t slot;
@@ -82,6 +96,15 @@ __global__ void __launch_bounds__(512) ubench(int iters, long long* out, int tme
       for (int c = 0; c < 4; ++c) { ld_32x32b_x8(tb + col + 8 * c, va, 8 * c); ld_32x32b_x8(tb + col + 32 + 8 * c, vb, 8 * c); }
       tmem_ld_wait32(va); tmem_ld_wait32(vb);
       acc += __uint_as_float(va[i & 31]) + __uint_as_float(vb[i & 31]);
+    } else if (MODE == 8) {  // one packed load covers the whole 64-column block (are 16-bit S accumulators cheaper to read?)
+      ld_32x32b_x32_pack16(tb + col, va);
+      tmem_ld_wait32(va);
+      acc += __uint_as_float(va[i & 31]);
+    } else if (MODE == 9) {  // packed load + 64 ex2
+      ld_32x32b_x32_pack16(tb + col, va);
+      tmem_ld_wait32(va);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc += fast_exp2(__uint_as_float(va[k]) * 1e-9f) + fast_exp2(__uint_as_float(va[k] << 16) * 1e-9f);
     } else if (MODE == 7) {  // 16x256b + 64 ex2
       ld_16x256b_x8(tb + col, va); ld_16x256b_x8(tb + col + (16u << 16), vb);
       tmem_ld_wait32(va); tmem_ld_wait32(vb);
@@ -131,5 +154,7 @@ int main() {
   for (int c : {1, 2}) for (int w : {4, 8}) run<5>("ld 16x128b.x16 x2 + wait", w, c);
   for (int c : {1, 2}) for (int w : {4, 8}) run<6>("ld 32x32b.x8 x8 + wait", w, c);
   for (int c : {1, 2}) for (int w : {4, 8}) run<7>("ld 16x256b + 64 ex2", w, c);
+  for (int c : {1, 2}) for (int w : {1, 4, 8}) run<8>("ld 32x32b.x32.pack16 (64 col)", w, c);
+  for (int c : {1, 2}) for (int w : {4, 8}) run<9>("ld pack16 + 64 ex2", w, c);
   return 0;
 }
