@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XS_LIB_PATH") or os.path.join(HERE, "libcrossscore_sm100a.so")  # override: development builds
 
-DT_BF16, DT_F32, DT_TF32 = 0, 1, 2
+DT_BF16, DT_F32, DT_TF32, DT_F16 = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY = 0, 1, 2, 3
 OP_PATCH_EMBED = 1
 

@@ -82,7 +82,7 @@ int gemm_tc(const void*, int, const void*, int, const float*, void*, int, int, i
 int head_jigsaw_tc(const void*, int, const void*, int, const float*, float*, int, int, int, int, int, float, int,
                    cudaStream_t);
 int flash_attn_bf16_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long,
-                       long long, long long, long long, int, int, int, float, cudaStream_t);
+                       long long, long long, long long, int, int, int, float, int, cudaStream_t);
 int gemm_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, cudaStream_t);
 int head_jigsaw_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, float,
                     cudaStream_t);
@@ -182,9 +182,11 @@ int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw
 int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                      int N, int K, int act, int dtype, int out_dtype, xs_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  XS_CHECK_ARG(out_dtype == XS_BF16 || out_dtype == XS_F32, "gemm: out_dtype must be bf16 or fp32");
+  XS_CHECK_ARG(out_dtype == XS_BF16 || out_dtype == XS_F32 || out_dtype == XS_F16,
+               "gemm: out_dtype must be bf16, fp16 or fp32");
   if (dtype == XS_BF16 || dtype == XS_TF32)
-    return gemm_tc(A, lda, W, ldw, bias, out, ldc, M, N, K, act, dtype == XS_TF32, out_dtype == XS_F32, st);
+    return gemm_tc(A, lda, W, ldw, bias, out, ldc, M, N, K, act, dtype == XS_TF32,
+                   out_dtype == XS_F32 ? 1 : (out_dtype == XS_F16 ? 3 : 0), st);
   if (dtype == XS_F32) {
     XS_CHECK_ARG(out_dtype == XS_F32, "gemm(fp32): output must be fp32");
     return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias,
@@ -206,10 +208,10 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
                   long long kv_row_stride, long long kv_batch_stride, int kv_shared, int nsplit, int o_is_f32,
                   float scale, int dtype, xs_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == XS_BF16) {
-    XS_CHECK_ARG(head_slot == 64, "flash_attn(bf16): head_slot must be 64, got %d", head_slot);
+  if (dtype == XS_BF16 || dtype == XS_F16) {
+    XS_CHECK_ARG(head_slot == 64, "flash_attn(16-bit): head_slot must be 64, got %d", head_slot);
     return flash_attn_bf16_tc(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, q_row_stride, q_batch_stride,
-                              kv_row_stride, kv_batch_stride, kv_shared, nsplit, o_is_f32, scale, st);
+                              kv_row_stride, kv_batch_stride, kv_shared, nsplit, o_is_f32, scale, dtype == XS_F16, st);
   }
   if (dtype == XS_F32) {
     XS_CHECK_ARG(o_is_f32, "flash_attn(fp32): output must be fp32");

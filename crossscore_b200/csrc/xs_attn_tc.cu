@@ -43,6 +43,7 @@ constexpr int ATT_REGS_SOFTMAX = 200;                   // setmaxnreg budgets (m
 constexpr int ATT_REGS_CTRL = 56;
 constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK runs ATT_NS blocks ahead of PV)
 constexpr float ATT_SUM_LIMIT = 65536.0f;                // a block row-sum of P above this (vs the stale max) forces a rescale
+constexpr float ATT_SUM_LIMIT_F16 = 2048.0f;             // fp16 variant: P and its packed-half partial sums stay below 65504
 constexpr uint32_t ATT_Q_BYTES = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16], 128B swizzle
 constexpr uint32_t ATT_KV_BYTES = ATT_BKV * 64 * 2;     // 8 KB:  [64 keys][64 bf16]
 constexpr uint32_t ATT_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_ST * ATT_KV_BYTES + 256 + 1024;
@@ -168,7 +169,14 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const AttnParams& p) 
 }
 
 // MODE 0: production; 1: phase clocks (XS_ATTN_PROF=1); 2: timing experiments that break the result (XS_ATTN_DBG=mask)
-template <int DQK_STEPS, int DV, int MODE>
+// F16: q/k/v are fp16, S = Q K^T is accumulated in FP16 (tcgen05 D format f16: one value per TMEM column, read two
+// columns per register with tcgen05.ld.pack::16b at 1.75x the column rate of the fp32 load), the softmax runs on
+// packed halves (HFMA2 / MUFU.EX2.F16x2 / HADD2: 3 instructions per two logits instead of 5 and no pack step), P is
+// fp16.  The fp32 variant above is bound by the TMEM read of S (tcgen05.ld, ~60 % busy next to the 62 % busy MUFU);
+// this one moves the bound to the MUFU alone.  Precision: logits rounded to fp16 is what the reference's own GPU path
+// (16-mixed autocast, config/default_predict.yaml:25) does; the host folds scale*log2(e) into the query projection so
+// that scale_log2 == 1 and the logits are small (tools/bf16_error_budget.py f16: error below the bf16-P variant).
+template <int DQK_STEPS, int DV, int MODE, bool F16 = false>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnParams p) {
@@ -255,8 +263,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == 5) {
     // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BKV, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major ([kv][d], d contiguous)
+    constexpr uint32_t idesc_qk = F16 ? umma_idesc_f16(128, ATT_BKV, 0, 0, 0) : umma_idesc_bf16(128, ATT_BKV, 0, 0);
+    // B = V is MN-major ([kv][d], d contiguous)
+    constexpr uint32_t idesc_pv = F16 ? umma_idesc_f16(128, DV, 0, 1, 1) : umma_idesc_bf16(128, DV, 0, 1);
     const uint32_t tb = warp_uniform(tmem_base);
     const uint32_t q_lo = umma_desc_lo(smem_u32(smQ), 16);
     const uint32_t k_lo0 = umma_desc_lo(smem_u32(smK), 16);
@@ -324,6 +333,193 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     pc.flush(p.prof, 8, lane);
   } else if (warp < 4) {
     reg_alloc<ATT_REGS_SOFTMAX>();
+    if constexpr (F16) {
+    // ===================== fp16 softmax / correction / epilogue (thread == query row) =====================
+    const int q = warp;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_o = tmem_O + lane_off;
+    const uint32_t sl2h = h2_bcast(p.scale_log2);
+    const float sl2 = h2_lo(sl2h);  // the scale the exponentials actually use (1.0 exactly with folded weights)
+    PhaseClock<PROF> pc;
+    pc.start();
+    uint32_t g0 = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      int nkv, tail_valid;
+      {
+        const TileCoord t = decode_tile(tile, p);
+        nkv = t.nkv;
+        tail_valid = t.kv_end - t.kv_begin - (t.nkv - 1) * ATT_BKV;
+      }
+      float m = -INFINITY;  // reference max (log2 domain), always exactly representable in fp16; may be stale
+      float l = 0.f;
+      int pending_sb = -1;
+      auto flush_pending = [&]() {
+        if (pending_sb >= 0) {
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full + pending_sb);
+          pending_sb = -1;
+        }
+      };
+      // One packed load brings a whole 64-key block (32 registers); the next block's load is in flight during the
+      // current block's exponentials (S is triple-buffered).
+      uint32_t va[32], vb[32];
+      if (lane == 0) mbar_wait(s_full + (g0 % ATT_NS), (g0 / ATT_NS) & 1);
+      __syncwarp();
+      tc_fence_after();
+      tmem_ld32_pack16(tmem_base + lane_off + (g0 % ATT_NS) * 64, va);
+      pc.lap(0);
+
+      auto block = [&](const int j, uint32_t (&cur)[32], uint32_t (&nxt)[32], auto mask_tag) __attribute__((always_inline)) {
+        constexpr bool MASK = decltype(mask_tag)::value;
+        const uint32_t g = g0 + j;
+        const uint32_t sb = g % ATT_NS;
+        const uint32_t t_s = tmem_base + lane_off + sb * 64;
+        tmem_ld_wait32(cur);
+        pc.lap(1);
+        if (j + 1 < nkv) {
+          const uint32_t sn = (g + 1) % ATT_NS;
+          if (lane == 0) mbar_wait(s_full + (sn), ((g + 1) / ATT_NS) & 1);
+          __syncwarp();
+          tc_fence_after();
+          tmem_ld32_pack16(tmem_base + lane_off + sn * 64, nxt);
+        }
+        pc.lap(0);
+        if constexpr (MASK) {  // keys >= tail_valid are past the sequence end: -inf (fp16 0xFC00)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (2 * i >= tail_valid) cur[i] = 0xFC00FC00u;
+            else if (2 * i + 1 >= tail_valid) cur[i] = (cur[i] & 0x0000FFFFu) | 0xFC000000u;
+          }
+        }
+        uint32_t pk[32];
+        uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;  // packed-half partial row sums (8 pairs each)
+        const uint32_t negm = h2_bcast(-m);
+        if (j > 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            pk[i] = h2_ex2(h2_fma(cur[i], sl2h, negm)); a0 = h2_add(a0, pk[i]);
+            pk[i + 1] = h2_ex2(h2_fma(cur[i + 1], sl2h, negm)); a1 = h2_add(a1, pk[i + 1]);
+            pk[i + 2] = h2_ex2(h2_fma(cur[i + 2], sl2h, negm)); a2 = h2_add(a2, pk[i + 2]);
+            pk[i + 3] = h2_ex2(h2_fma(cur[i + 3], sl2h, negm)); a3 = h2_add(a3, pk[i + 3]);
+          }
+        }
+        flush_pending();  // previous block's P: its tcgen05.st has long landed
+        if (j > 0) {
+#pragma unroll
+          for (int i = 16; i < 32; i += 4) {
+            pk[i] = h2_ex2(h2_fma(cur[i], sl2h, negm)); a0 = h2_add(a0, pk[i]);
+            pk[i + 1] = h2_ex2(h2_fma(cur[i + 1], sl2h, negm)); a1 = h2_add(a1, pk[i + 1]);
+            pk[i + 2] = h2_ex2(h2_fma(cur[i + 2], sl2h, negm)); a2 = h2_add(a2, pk[i + 2]);
+            pk[i + 3] = h2_ex2(h2_fma(cur[i + 3], sl2h, negm)); a3 = h2_add(a3, pk[i + 3]);
+          }
+        }
+        uint32_t at = h2_add(h2_add(a0, a1), h2_add(a2, a3));
+        float bsum = h2_lo(at) + h2_hi(at);
+        // Stale reference max, as in the fp32 variant: the block's row sum is the overflow detector (a P beyond
+        // the fp16 range makes it inf).  The limit keeps every partial sum inside fp16.
+        const bool need = (j == 0) || !(bsum <= ATT_SUM_LIMIT_F16);
+        if (__any_sync(0xffffffffu, need)) {
+          pc.lap(2);
+          uint32_t mx2 = cur[0];
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx2 = h2_max(mx2, cur[i]);
+          const float mx = fmaxf(h2_lo(mx2), h2_hi(mx2)) * sl2;
+          float m_new = need ? fmaxf(mx, m) : m;
+          m_new = h2_lo(h2_bcast(m_new));  // keep m representable in fp16 (exact when scale_log2 == 1)
+          const float alpha = fast_exp2(m - m_new);  // 1 when unchanged, 0 when m was -inf
+          l *= alpha;
+          if (j > 0) {
+            if (lane == 0) mbar_wait(kv_empty + ((g - 1) % ATT_ST), ((g - 1) / ATT_ST) & 1);  // PV_{g-1} complete
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < DV / 16; ++c) {
+              uint32_t v[16];
+              tmem_ld16(t_o + c * 16, v);
+              tmem_ld_wait16(v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st16(t_o + c * 16, v);
+            }
+          }
+          m = m_new;
+          const uint32_t negm2 = h2_bcast(-m);
+          a0 = a1 = a2 = a3 = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            pk[i] = h2_ex2(h2_fma(cur[i], sl2h, negm2)); a0 = h2_add(a0, pk[i]);
+            pk[i + 1] = h2_ex2(h2_fma(cur[i + 1], sl2h, negm2)); a1 = h2_add(a1, pk[i + 1]);
+            pk[i + 2] = h2_ex2(h2_fma(cur[i + 2], sl2h, negm2)); a2 = h2_add(a2, pk[i + 2]);
+            pk[i + 3] = h2_ex2(h2_fma(cur[i + 3], sl2h, negm2)); a3 = h2_add(a3, pk[i + 3]);
+          }
+          at = h2_add(h2_add(a0, a1), h2_add(a2, a3));
+          bsum = h2_lo(at) + h2_hi(at);
+          pc.lap(7);
+        }
+        l += bsum;
+        pc.lap(2);
+        tmem_st32(t_s + 32, pk);  // P_g (64 halves) over the upper half of S_sb, whose logits are all in registers
+        pending_sb = static_cast<int>(sb);
+        pc.lap(3);
+      };
+      {
+        int j = 0;
+        for (; j + 2 < nkv; j += 2) {
+          block(j, va, vb, MaskNo{});
+          block(j + 1, vb, va, MaskNo{});
+        }
+        if (j + 2 == nkv) {
+          block(j, va, vb, MaskNo{});
+          block(j + 1, vb, va, MaskYes{});
+        } else {
+          block(j, va, vb, MaskYes{});
+        }
+      }
+      flush_pending();
+      g0 += nkv;
+
+      // ---- epilogue: O / l and log-sum-exp (same as the fp32-logit variant) ----
+      if (lane == 0) mbar_wait(o_full, it & 1);
+      __syncwarp();
+      pc.lap(4);
+      tc_fence_after();
+      tmem_ld32(t_o, va);
+      if constexpr (DV == 64) tmem_ld32(t_o + 32, vb);
+      else tmem_ld16_lo(t_o + 32, vb);
+      tmem_ld_wait32(va);
+      tmem_ld_wait32(vb);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      const float inv = 1.0f / l;
+      const TileCoord t = decode_tile(tile, p);
+      const int row_g = t.q0 + row;
+      const long long o_off = static_cast<long long>(t.split) * p.o_split_stride +
+                              static_cast<long long>(t.b) * p.o_batch_stride +
+                              static_cast<long long>(row_g) * p.o_row_stride + static_cast<long long>(t.h) * DV;
+      if (row_g < p.Lq) {
+        if (p.o_is_f32) {
+          float* dst = reinterpret_cast<float*>(p.o) + o_off;
+          store_row_f32<0, 32>(dst, va, inv);
+          store_row_f32<0, DV - 32>(dst + 32, vb, inv);
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.o) + o_off;
+          store_row_bf16<0, 32>(dst, va, inv);
+          store_row_bf16<0, DV - 32>(dst + 32, vb, inv);
+        }
+        if (p.lse != nullptr) {
+          p.lse[static_cast<long long>(t.split) * p.lse_split_stride +
+                (static_cast<long long>(t.b) * p.heads + t.h) * p.Lq + row_g] = (m + log2f(l)) * 0.6931471805599453f;
+        }
+      }
+      pc.lap(5);
+    }
+    pc.flush(p.prof, 0, lane);
+    pc.flush(p.prof, 16 + 8 * warp, lane);
+    } else {
     // ===================== softmax / correction / epilogue (thread == query row) =====================
     const int q = warp;  // TMEM lane quarter accessible to this warp (warp id % 4)
     const int row = q * 32 + lane;
@@ -500,6 +696,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     pc.flush(p.prof, 0, lane);
     pc.flush(p.prof, 16 + 8 * warp, lane);  // per lane-quarter copy
+    }
   }
 
   tc_fence_before();
@@ -551,10 +748,11 @@ static int launch_attn_prof(int head_dim, dim3 grid, const CUtensorMap& tmQ, con
 
 // q/k/v: bf16, head h occupies 64 consecutive columns starting at h*64 of its row (d=48: 48 used + 16 pad)
 // strides in elements.  o: [nsplit][B][Lq][heads*head_dim] (bf16, or fp32 when o_is_f32)
+// operands_f16: q/k/v are fp16 and the fp16-logit kernel runs (see attn_tc_kernel<..., F16>)
 int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq,
                        int Lk, int head_dim, long long q_row_stride, long long q_batch_stride,
                        long long kv_row_stride, long long kv_batch_stride, int kv_shared, int nsplit, int o_is_f32,
-                       float scale, cudaStream_t stream) {
+                       float scale, int operands_f16, cudaStream_t stream) {
   XS_CHECK_ARG(head_dim == 64 || head_dim == 48, "flash_attn: head_dim %d not supported (64 or 48)", head_dim);
   XS_CHECK_ARG(B > 0 && heads > 0 && Lq > 0 && Lk > 0 && nsplit > 0, "flash_attn: empty problem");
   XS_CHECK_ARG((q_row_stride % 8) == 0 && (kv_row_stride % 8) == 0 && (q_batch_stride % 8) == 0 &&
@@ -613,6 +811,44 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
   if (dbg < 0) {
     const char* e = getenv("XS_ATTN_DBG");
     dbg = e ? atoi(e) : 0;
+  }
+  if (operands_f16) {
+    if (prof) {  // phase clocks of the fp16 variant (XS_ATTN_PROF=1)
+      static unsigned long long* buf = nullptr;
+      if (buf == nullptr) XS_CUDA(cudaMalloc(&buf, 48 * sizeof(unsigned long long)));
+      XS_CUDA(cudaMemsetAsync(buf, 0, 48 * sizeof(unsigned long long), stream));
+      p.prof = buf;
+      if (head_dim == 64) {
+        auto kern = attn_tc_kernel<4, 64, 1, true>;
+        XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+        kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+      } else {
+        auto kern = attn_tc_kernel<3, 48, 1, true>;
+        XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+        kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+      }
+      XS_LAUNCH_CHECK();
+      XS_CUDA(cudaStreamSynchronize(stream));
+      unsigned long long h[48];
+      XS_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
+      const double ctas = double(p.n_tiles);
+      fprintf(stderr, "attn f16 prof (clk per tile): softmax warp: wait_S+ld_issue %.0f  ld_wait %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
+                      "epi %.0f  slow %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
+              h[0] / ctas / 4, h[1] / ctas / 4, h[2] / ctas / 4, h[3] / ctas / 4, h[4] / ctas / 4, h[5] / ctas / 4,
+              h[7] / ctas / 4, h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
+      return 0;
+    }
+    if (head_dim == 64) {
+      auto kern = attn_tc_kernel<4, 64, 0, true>;
+      XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+      kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    } else {
+      auto kern = attn_tc_kernel<3, 48, 0, true>;
+      XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+      kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    }
+    XS_LAUNCH_CHECK();
+    return 0;
   }
   if (head_dim == 64) p.dbg = dbg;
   if (dbg && !prof && head_dim == 64) {  // development: timing experiments on the d=64 shape

@@ -37,7 +37,7 @@ void set_last_error(const char* fmt, ...);
 
 #define XS_LAUNCH_CHECK() XS_CUDA(cudaGetLastError())
 
-enum DType : int { XS_BF16 = 0, XS_F32 = 1, XS_TF32 = 2 };
+enum DType : int { XS_BF16 = 0, XS_F32 = 1, XS_TF32 = 2, XS_F16 = 3 };
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_LEAKY = 3 };
 
 int num_sms();
@@ -70,6 +70,12 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
+  return r;
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -270,13 +276,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
-// TMA reduce-store: global[tile] += smem tile (element type of the tensor map, here fp32), performed at the L2
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(tm)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -371,6 +370,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4)                                 // D format f32
          | (1u << 7)                               // A format bf16
          | (1u << 10)                              // B format bf16
+         | (static_cast<uint32_t>(a_mn_major) << 15)
+         | (static_cast<uint32_t>(b_mn_major) << 16)
+         | (static_cast<uint32_t>(N >> 3) << 17)
+         | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// kind::f16 with fp16 A/B; D is fp16 (d_f32 = 0) or fp32.  (fp16 accumulators are only legal with fp16 operands, and
+// the A / B formats cannot be mixed: both measured, tools/ubench_f16acc.cu.)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int d_f32) {
+  return (static_cast<uint32_t>(d_f32) << 4)
          | (static_cast<uint32_t>(a_mn_major) << 15)
          | (static_cast<uint32_t>(b_mn_major) << 16)
          | (static_cast<uint32_t>(N >> 3) << 17)
@@ -598,6 +607,65 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// 64 TMEM columns holding one 16-bit value each (fp16 accumulators) -> 32 registers: .pack::16b puts column 2i in the
+// low and column 2i+1 in the high half of register i (1.75x the column rate of the unpacked load, measured)
+__device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> TMEM, 32 lanes x 32 columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// packed half (f16x2) arithmetic on raw 32-bit registers
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_ex2(uint32_t a) {  // one MUFU instruction, two exponentials
+  uint32_t d;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ float h2_lo(uint32_t a) {
+  float f;
+  asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(f) : "r"(a));
+  return f;
+}
+__device__ __forceinline__ float h2_hi(uint32_t a) {
+  float f;
+  asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, hi;}" : "=f"(f) : "r"(a));
+  return f;
+}
+__device__ __forceinline__ uint32_t h2_bcast(float v) { return pack_f16x2(v, v); }
 #endif  // __CUDACC__
 
 }  // namespace xs

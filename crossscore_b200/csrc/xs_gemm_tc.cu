@@ -34,7 +34,13 @@ constexpr int JIG_LD = 197;          // padded row length of the fp32 score stag
 
 enum Epi : int { EPI_STORE = 0, EPI_JIGSAW = 1 };
 enum InT : int { IN_BF16 = 0, IN_TF32 = 1 };
-enum OutT : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ADD = 2 };  // ADD: out += tile (TMA reduce-store, fp32)
+// ADD: out (fp32) += tile, in place; F16: fp16 output (q|k|v operands of the fp16 attention kernel)
+enum OutT : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ADD = 2, OUT_F16 = 3 };
+template <int OUT>
+__device__ __forceinline__ uint32_t pack_out16(float lo, float hi) {
+  if constexpr (OUT == OUT_F16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
 
 struct JigsawParams {
   float* score;  // (B, 14*ph, 14*pw) fp32
@@ -49,7 +55,7 @@ struct JigsawParams {
 template <int BN, int STAGES, int EPI, int CTA2 = 0, int OUT = 0>
 struct GemmSmem {
   // one 32-row x 32-column staging tile of an epilogue warp (64-byte rows for bf16 output, 128-byte rows for fp32)
-  static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * (OUT != 0 ? 4 : 2);
+  static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * ((OUT == 1 || OUT == 2) ? 4 : 2);
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * GEMM_BK * 2;  // a CTA pair splits the W tile rows
   static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4;
@@ -58,7 +64,7 @@ struct GemmSmem {
   static constexpr uint32_t OFF_B = OFF_A + A_SLOTS * A_BYTES;
   static constexpr uint32_t OFF_STAGING = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_BAR = (OFF_STAGING + STAGING_BYTES + 15u) & ~15u;
-  static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4 + 2 * GEMM_KB_MAX) * 8 + 16;
+  static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4 + 2 * GEMM_KB_MAX + 16) * 8 + 16;  // +16: residual-tile barriers
   static constexpr uint32_t TOTAL = OFF_BAR + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment of the base
 };
 
@@ -94,7 +100,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* a_full = tmem_empty + 2;            // [GEMM_KB_MAX] A-stationary mode only
   uint64_t* a_empty = a_full + GEMM_KB_MAX;     // [GEMM_KB_MAX]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + GEMM_KB_MAX);
+  uint64_t* res_full = a_empty + GEMM_KB_MAX;   // [8 epilogue warps][2] OUT_F32_ADD only: residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
   constexpr bool ASTAT = CTA2 == 2;
 
   const int warp = threadIdx.x >> 5;
@@ -126,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
     }
+    for (int s = 0; s < 16; ++s) mbar_init(&res_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -268,17 +276,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;          // row of the tile owned by this thread
     uint32_t acc_stage = 0, acc_phase = 0;
     uint32_t chunk_counter = 0;
-    for (int i = 0; i < my_count; ++i) {
-      int m_tile, n_blk;  // (pair) row block and n-tile of this worker's i-th tile
+    // (row block, n-tile) of this worker's t-th tile
+    auto tile_coords = [&](int t, int& m_blk_o, int& n_blk_o) {
+      int m_tile;
       if constexpr (ASTAT) {
-        m_tile = worker + (i / num_n) * n_workers;
-        n_blk = i % num_n;
+        m_tile = worker + (t / num_n) * n_workers;
+        n_blk_o = t % num_n;
       } else {
-        const int tile = worker + i * n_workers;
+        const int tile = worker + t * n_workers;
         m_tile = tile / num_n;
-        n_blk = tile % num_n;
+        n_blk_o = tile % num_n;
       }
-      const int m_blk = m_tile * NC + static_cast<int>(rank);
+      m_blk_o = m_tile * NC + static_cast<int>(rank);
+    };
+    // OUT_F32_ADD (out += tile): every epilogue warp fetches the 32 x 32 fp32 tile of the residual stream its next
+    // step will update with a TMA load into the step's staging buffer, ONE STEP AHEAD (across tile boundaries: the
+    // first load of a tile is in flight during that tile's mainloop), adds in shared memory and stores the tile
+    // back.  (A TMA reduce-store (UTMAREDG.ADD) does the same add at the L2 without the load, but its throughput
+    // capped these GEMMs: proj 0.083 -> 0.174 ms, fc2 0.230 -> 0.305 ms, measured.)
+    uint64_t* my_res_full = res_full + (warp - 4) * 2;
+    auto issue_res_load = [&](uint32_t step_idx) {  // one lane
+      if constexpr (OUT == OUT_F32_ADD && EPI == EPI_STORE) {
+        constexpr int MY_STEPS_ = BN / 64;
+        const int t = static_cast<int>(step_idx / MY_STEPS_), sidx = static_cast<int>(step_idx % MY_STEPS_);
+        if (t >= my_count) return;
+        int mb, nb;
+        tile_coords(t, mb, nb);
+        const uint32_t b = step_idx & 1;
+        uint8_t* dst = staging + (warp - 4) * (2 * L::WARP_STAGE_BYTES) + b * L::WARP_STAGE_BYTES;
+        mbar_expect_tx(&my_res_full[b], L::WARP_STAGE_BYTES);
+        tma_load_2d(dst, &tmC, &my_res_full[b], nb * BN + (2 * sidx + half) * 32, mb * GEMM_BM + q * 32);
+      }
+    };
+    if constexpr (OUT == OUT_F32_ADD && EPI == EPI_STORE) {
+      if (lane == 0) issue_res_load(0);
+    }
+    for (int i = 0; i < my_count; ++i) {
+      int m_blk, n_blk;
+      tile_coords(i, m_blk, n_blk);
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc_stage * ACC_STAGE_COLS + (static_cast<uint32_t>(q * 32) << 16);
@@ -309,15 +344,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           const uint32_t buf = chunk_counter & 1;
-          ++chunk_counter;
-          // the TMA store that last read this staging buffer (two steps ago) must have drained
-          if (lane == 0) tma_store_wait_read<1>();
+          if constexpr (OUT == OUT_F32_ADD) {
+            // the other buffer was last read by the previous step's store: once that has drained, fetch the next
+            // step's residual tile into it; then wait for this step's tile (requested one step ago)
+            if (lane == 0) {
+              tma_store_wait_read<0>();
+              issue_res_load(chunk_counter + 1);
+            }
+            mbar_wait(&my_res_full[buf], (chunk_counter >> 1) & 1);
+          } else {
+            // the TMA store that last read this staging buffer (two steps ago) must have drained
+            if (lane == 0) tma_store_wait_read<1>();
+          }
           __syncwarp();
+          ++chunk_counter;
           const int n0 = n_blk * BN + c * 32;
           uint8_t* srow = my_staging + buf * L::WARP_STAGE_BYTES;
           const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
           const uint32_t(&vv)[32] = v[i & 1];
-          if constexpr (OUT == OUT_BF16) {
+          if constexpr (OUT == OUT_BF16 || OUT == OUT_F16) {
             // 64-byte rows, 64B swizzle: 16-byte chunk index XOR ((row >> 1) & 3); conflict-free for thread == row
             uint8_t* rp = srow + lane * 64;
 #pragma unroll
@@ -325,13 +370,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 ba = __ldg(b4 + j * 2), bb = __ldg(b4 + j * 2 + 1);
               const int o = j * 8;
               uint4 pk;
-              pk.x = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 0]) + ba.x),
+              pk.x = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 0]) + ba.x),
                                  apply_act<ACT>(__uint_as_float(vv[o + 1]) + ba.y));
-              pk.y = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 2]) + ba.z),
+              pk.y = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 2]) + ba.z),
                                  apply_act<ACT>(__uint_as_float(vv[o + 3]) + ba.w));
-              pk.z = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 4]) + bb.x),
+              pk.z = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 4]) + bb.x),
                                  apply_act<ACT>(__uint_as_float(vv[o + 5]) + bb.y));
-              pk.w = pack_bf16x2(apply_act<ACT>(__uint_as_float(vv[o + 6]) + bb.z),
+              pk.w = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 6]) + bb.z),
                                  apply_act<ACT>(__uint_as_float(vv[o + 7]) + bb.w));
               *reinterpret_cast<uint4*>(rp + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
             }
@@ -346,15 +391,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               o4.y = apply_act<ACT>(__uint_as_float(vv[j * 4 + 1]) + ba.y);
               o4.z = apply_act<ACT>(__uint_as_float(vv[j * 4 + 2]) + ba.z);
               o4.w = apply_act<ACT>(__uint_as_float(vv[j * 4 + 3]) + ba.w);
-              *reinterpret_cast<float4*>(rp + ((j ^ (lane & 7)) << 4)) = o4;
+              float4* sp = reinterpret_cast<float4*>(rp + ((j ^ (lane & 7)) << 4));
+              if constexpr (OUT == OUT_F32_ADD) {  // the residual tile sits in the same swizzled layout
+                const float4 r4 = *sp;
+                o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
+              }
+              *sp = o4;
             }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             // box = 32 columns x 32 rows; clips the M tail
-            if constexpr (OUT == OUT_F32_ADD) tma_reduce_add_2d(&tmC, srow, n0, m0);  // residual stream += tile
-            else tma_store_2d(&tmC, srow, n0, m0);
+            tma_store_2d(&tmC, srow, n0, m0);
             tma_store_commit();
           }
         }
@@ -432,7 +481,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
                        int N, int K, JigsawParams jp, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT>;
   constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
-  constexpr int OUT_B = (OUT != OUT_BF16) ? 4 : 2;
+  constexpr int OUT_B = (OUT == OUT_F32 || OUT == OUT_F32_ADD) ? 4 : 2;
   constexpr uint32_t BKE = 128 / IN_B;
   CUtensorMap tmA, tmW, tmC;
   {
@@ -503,7 +552,7 @@ static int dispatch_act(const void* A, int lda, const void* W, int ldw, const fl
 }
 
 // Tensor-core GEMM entry used by xs_api.cu.  in_tf32: A/W are fp32 (TF32 multiply), else bf16.
-// out_f32: 0 bf16 output, 1 fp32 output, 2 fp32 output accumulated in place (out += ...).
+// out_f32: 0 bf16 output, 1 fp32 output, 2 fp32 output accumulated in place (out += ...), 3 fp16 output.
 // N must be a multiple of 192 or 256; row pitches must be multiples of 16 bytes.
 int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M, int N, int K,
             int act, int in_tf32, int out_f32, cudaStream_t stream) {
@@ -518,6 +567,31 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
                "gemm: pointers must be 16-byte aligned");
   const bool use192 = (N % 192 == 0) && (N % 256 != 0 || N < 1024);
   XS_CHECK_ARG(use192 || N % 256 == 0, "gemm: N=%d must be a multiple of 192 or 256 (pad the weight rows)", N);
+  if (!in_tf32 && out_f32 == 3) {
+    // bf16 operands, fp16 result (fused q|k|v and the decoder K/V cache feeding the fp16 attention kernel): same
+    // kernel selection as the bf16-output path below
+    XS_CHECK_ARG(act == ACT_NONE, "gemm: fp16 output supports act=NONE only");
+    JigsawParams jp{};
+    const int bn = use192 ? 192 : 256;
+    const int num_m2 = (M + 255) / 256;
+    const bool fits = num_m2 * (N / bn) >= num_sms() / 2;
+    if (K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2) {
+      if (use192) return launch_gemm<192, 8, EPI_STORE, ACT_NONE, IN_BF16, OUT_F16, 2>(XS_GEMM_ARGS);
+      return launch_gemm<256, 6, EPI_STORE, ACT_NONE, IN_BF16, OUT_F16, 2>(XS_GEMM_ARGS);
+    }
+    if (fits && K >= 1024) {
+      if (use192) return launch_gemm<192, 6, EPI_STORE, ACT_NONE, IN_BF16, OUT_F16, 1>(XS_GEMM_ARGS);
+      return launch_gemm<256, 6, EPI_STORE, ACT_NONE, IN_BF16, OUT_F16, 1>(XS_GEMM_ARGS);
+    }
+    if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F16>(XS_GEMM_ARGS);
+    return launch_gemm<256, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F16>(XS_GEMM_ARGS);
+  }
+  if (in_tf32 && out_f32 == 3) {  // tf32 operands, fp16 result (decoder Q/K/V projections)
+    XS_CHECK_ARG(act == ACT_NONE, "gemm: tf32->fp16 supports act=NONE only");
+    JigsawParams jp{};
+    if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_TF32, OUT_F16>(XS_GEMM_ARGS);
+    return launch_gemm<256, 3, EPI_STORE, ACT_NONE, IN_TF32, OUT_F16>(XS_GEMM_ARGS);
+  }
   if (!in_tf32 && !out_f32) {
     // CTA pairs for the long-K GEMM (fc2, K = 1536: 1.35 PF vs 1.13 PF single-CTA, measured); the K = 384 GEMMs
     // are bound by their epilogue / operand refill per tile and run faster as independent CTAs.
@@ -547,8 +621,8 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
   JigsawParams jp{};
   if (!in_tf32 && out_f32 == 2) {
     // bf16 operands, out (fp32) += A W^T + bias: the residual add of the DINOv2 blocks (attention.output.dense and
-    // mlp.fc2 with LayerScale folded in, modeling_dinov2.py:367-386) done by the TMA reduce-store of the epilogue,
-    // so the delta never exists in HBM and the LayerNorm that follows reads the residual stream only
+    // mlp.fc2 with LayerScale folded in, modeling_dinov2.py:367-386) done in the epilogue (residual tile prefetched
+    // by TMA), so the delta never exists in HBM and the LayerNorm that follows reads the residual stream only
     XS_CHECK_ARG(act == ACT_NONE, "gemm: residual accumulate supports act=NONE only");
     XS_CHECK_ARG(use192, "gemm: residual accumulate needs N %% 192 == 0 (N=%d)", N);
     static int pair_mode = -1;

@@ -7,6 +7,8 @@
 // model/customised_transformer/transformer.py:78-80,159-173), CLS cat + pos-emb add (modeling_dinov2.py:108-112),
 // CLS drop / query-ref split (task/core.py:142-153), MultiViewPosionalEmbeddings
 // (model/positional_encoding.py:42-75), bicubic pos-emb resample (modeling_dinov2.py:57-95).
+#include <cuda_fp16.h>
+
 #include "xs_common.cuh"
 
 namespace xs {
@@ -480,6 +482,13 @@ int rows_attn_probs(const void* q, const void* k, const float* lse, float* probs
                     long long kv_row_stride, long long kv_batch_stride, float scale, int dtype, cudaStream_t stream) {
   XS_CHECK_ARG(B > 0 && Lq > 0 && Lk > 0 && head >= 0 && head < heads, "attn_probs: bad dims / head id %d", head);
   const long long total = static_cast<long long>(B) * Lq * Lk;
+  if (dtype == XS_F16) {  // fp16 q/k (the operands of the fp16 attention kernel)
+    attn_probs_kernel<__half><<<grid_for(total), 256, 0, stream>>>(
+        static_cast<const __half*>(q), static_cast<const __half*>(k), lse, probs, B, heads, head, Lq, Lk, d, head_slot,
+        q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, scale);
+    XS_LAUNCH_CHECK();
+    return 0;
+  }
   XS_DISPATCH_AT(dtype, (attn_probs_kernel<AT><<<grid_for(total), 256, 0, stream>>>(
                             static_cast<const AT*>(q), static_cast<const AT*>(k), lse, probs, B, heads, head, Lq, Lk,
                             d, head_slot, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, scale)));

@@ -25,7 +25,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, DT_TF32, call
+from ._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F16, DT_F32, DT_TF32, call
 
 C = 384
 PATCH = 14
@@ -47,9 +47,17 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """Kernel-friendly copies of the reference state_dict (built once per device / precision)."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], device, precision: str, do_self_attn: bool = True):
+    def __init__(self, sd: Dict[str, torch.Tensor], device, precision: str, do_self_attn: bool = True,
+                 fold_qscale: bool = False):
+        """fold_qscale: multiply the query projections by softmax_scale * log2(e) (in fp32, before rounding), so the
+        attention kernel's logits are already in the log2 domain (fp16-logit attention: scale_log2 == 1 exactly and
+        the fp16 accumulators hold small numbers)."""
         assert precision in ("bf16", "fp32")
         self.precision = precision
+        self.fold_qscale = fold_qscale
+        LOG2E = 1.4426950408889634
+        qs_dino = LOG2E / math.sqrt(64.0) if fold_qscale else 1.0
+        qs_dec = LOG2E / math.sqrt(float(DEC_D)) if fold_qscale else 1.0
         self.dt = DT_BF16 if precision == "bf16" else DT_F32
         self.wdtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.slot = 64 if precision == "bf16" else DEC_D  # decoder head slot width
@@ -70,10 +78,11 @@ class PackedWeights:
             lam1, lam2 = f32(p + "layer_scale1.lambda1"), f32(p + "layer_scale2.lambda1")
             L = dict(
                 ln1_g=f32(p + "norm1.weight"), ln1_b=f32(p + "norm1.bias"),
-                wqkv=W(torch.cat([f32(p + "attention.attention.query.weight"),
+                wqkv=W(torch.cat([f32(p + "attention.attention.query.weight") * qs_dino,
                                   f32(p + "attention.attention.key.weight"),
                                   f32(p + "attention.attention.value.weight")], 0)),
-                bqkv=torch.cat([f32(p + "attention.attention.query.bias"), f32(p + "attention.attention.key.bias"),
+                bqkv=torch.cat([f32(p + "attention.attention.query.bias") * qs_dino,
+                                f32(p + "attention.attention.key.bias"),
                                 f32(p + "attention.attention.value.bias")], 0).contiguous(),
                 # LayerScale folded into the producing Linear in fp32, before any rounding:
                 #   h += lam * (a W^T + b)  ==  h += a (lam*W)^T + lam*b
@@ -108,11 +117,12 @@ class PackedWeights:
             D = {}
             if do_self_attn:
                 wi, bi = f32(p + "self_attn.in_proj_weight"), f32(p + "self_attn.in_proj_bias")
-                D["sa_win"] = WP(torch.cat([pad_heads(wi[i * C:(i + 1) * C]) for i in range(3)], 0))
-                D["sa_bin"] = torch.cat([pad_heads_b(bi[i * C:(i + 1) * C]) for i in range(3)], 0).contiguous()
+                qs = (qs_dec, 1.0, 1.0)
+                D["sa_win"] = WP(torch.cat([pad_heads(wi[i * C:(i + 1) * C] * qs[i]) for i in range(3)], 0))
+                D["sa_bin"] = torch.cat([pad_heads_b(bi[i * C:(i + 1) * C] * qs[i]) for i in range(3)], 0).contiguous()
                 D["sa_wo"], D["sa_bo"] = WP(f32(p + "self_attn.out_proj.weight")), f32(p + "self_attn.out_proj.bias")
             wi, bi = f32(p + "multihead_attn.in_proj_weight"), f32(p + "multihead_attn.in_proj_bias")
-            D["ca_wq"], D["ca_bq"] = WP(pad_heads(wi[:C])), pad_heads_b(bi[:C]).contiguous()
+            D["ca_wq"], D["ca_bq"] = WP(pad_heads(wi[:C] * qs_dec)), pad_heads_b(bi[:C] * qs_dec).contiguous()
             kv_w += [pad_heads(wi[C:2 * C]), pad_heads(wi[2 * C:])]
             kv_b += [pad_heads_b(bi[C:2 * C]), pad_heads_b(bi[2 * C:])]
             D["ca_wo"], D["ca_bo"] = WP(f32(p + "multihead_attn.out_proj.weight")), f32(p + "multihead_attn.out_proj.bias")
@@ -163,10 +173,15 @@ class Engine:
         _lib.load()
         with torch.cuda.device(device):
             call("xs_device_check")
-        self.w = PackedWeights(sd, device, precision, do_self_attn)
+        # bf16 product mode: attention runs on fp16 operands with fp16 logit accumulators (XS_ATTN_F16=0: the bf16 /
+        # fp32-logit kernel, kept for A/B measurements); everything else (GEMM operands, attention output) stays bf16
+        self.attn_f16 = precision == "bf16" and os.environ.get("XS_ATTN_F16", "1") != "0"
+        self.w = PackedWeights(sd, device, precision, do_self_attn, fold_qscale=self.attn_f16)
         self.device = device
         self.dt = self.w.dt
         self.adtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.qdtype = torch.float16 if self.attn_f16 else self.adtype   # q / k / v and the decoder K/V cache
+        self.attn_dt = DT_F16 if self.attn_f16 else self.dt
         self.do_self_attn, self.do_short_cut = do_self_attn, do_short_cut
         self.use_tanh, self.power = bool(use_tanh), float(power)
         self._ws = {}
@@ -212,7 +227,7 @@ class Engine:
             dt = DT_BF16
         else:
             dt = DT_TF32 if self.dt == DT_BF16 else DT_F32
-        odt = DT_BF16 if out.dtype == torch.bfloat16 else DT_F32
+        odt = {torch.bfloat16: DT_BF16, torch.float16: DT_F16, torch.float32: DT_F32}[out.dtype]
         flops = 2.0 * M * (n_real or N) * (k_real or K)  # algorithmic: padding is not counted
         with self._op(tag, flops):
             call("xs_gemm_bias_act", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(out),
@@ -235,11 +250,16 @@ class Engine:
             call("xs_layernorm", _ptr(res_in), _ptr(delta), _ptr(res_out), _ptr(g), _ptr(b), eps, _ptr(y), _ptr(y32),
                  rows, dt, st)
 
+    def attn_scale(self, d):
+        """Softmax scale the attention kernels are given: with the scale folded into the query projection the
+        logits are log2-domain already and the kernel's scale * log2(e) must be 1."""
+        return math.log(2.0) if self.w.fold_qscale else 1.0 / math.sqrt(d)
+
     def _attn(self, q, k, v, o, B, heads, Lq, Lk, d, slot, q_rs, q_bs, kv_rs, kv_bs, kv_shared, st,
               lse=None, name="att"):
         """q/k/v are tensor views whose data_ptr is the first column of the respective part; o is bf16 or
         fp32 (B*Lq, heads*d)."""
-        scale = 1.0 / math.sqrt(d)
+        scale = self.attn_scale(d)
         ctas = B * heads * ((Lq + 127) // 128)
         nblk = (Lk + 127) // 128
         nsplit = max(1, min((2 * NUM_SMS_HINT) // max(ctas, 1), nblk // 4))
@@ -250,13 +270,13 @@ class Engine:
         if nsplit == 1:
             with self._op("attn_" + name, flops):
                 call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), B, heads, Lq, Lk, d, slot,
-                     q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), 1, o_is_f32, scale, self.dt, st)
+                     q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), 1, o_is_f32, scale, self.attn_dt, st)
         else:  # small batch: split the keys across CTAs, then merge (same merge as the multi-GPU path)
             o_parts = self._buf(name + "_oparts", (nsplit, B * Lq, heads * d), torch.float32)
             l_parts = self._buf(name + "_lparts", (nsplit, B, heads, Lq), torch.float32)
             with self._op("attn_" + name, flops):
                 call("xs_flash_attn", _ptr(q), _ptr(k), _ptr(v), _ptr(o_parts), _ptr(l_parts), B, heads, Lq, Lk, d,
-                     slot, q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), nsplit, 1, scale, self.dt, st)
+                     slot, q_rs, q_bs, kv_rs, kv_bs, int(kv_shared), nsplit, 1, scale, self.attn_dt, st)
             with self._op("lse_merge", 0.0, o_parts.numel() * 4.0):
                 call("xs_lse_merge", _ptr(o_parts), _ptr(l_parts), _ptr(o), _ptr(lse), nsplit, B, Lq, heads, d, 0, 0,
                      DT_F32 if o_is_f32 else DT_BF16, st)
@@ -287,7 +307,7 @@ class Engine:
         R = I * T
         h = self._buf("h", (R, C), torch.float32)
         y = self._buf("y", (R, C), A)
-        qkv = self._buf("qkv", (R, 3 * C), A)
+        qkv = self._buf("qkv", (R, 3 * C), self.qdtype)
         att = self._buf("att", (R, C), A)
         d = self._buf("d", (R, C), A)
         g1 = self._buf("g", (R, 4 * C), A)
@@ -335,20 +355,48 @@ class Engine:
             nr = int(r.shape[0])
         H, Wd = groups[0].shape[-2:]
         ph, pw = H // PATCH, Wd // PATCH
-        h, d, I, P = self.backbone(groups, st)
+        P = ph * pw
         _, pe = w.tables(ph, pw, st)
         xq32 = self._buf("xq32", (nq * P, C), torch.float32) if nq else None
         mem = self._buf("mem", (nr * P, C), self.adtype) if nr and want_mem else None
         es = self.adtype.itemsize
-        with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + (es if d is not None else 0) + es)):
-            call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS, _ptr(pe),
-                 _ptr(xq32), None, _ptr(mem), I, nq, P, self.dt, st)
+        # The images are independent through the whole backbone, so it runs CHUNK BY CHUNK (all 12 layers for a few
+        # images at a time): the per-layer intermediates (y, qkv, att, g: 22 bytes per residual element) of a chunk
+        # then fit in the 126 MB L2 and producer -> consumer traffic stays on chip instead of going through HBM,
+        # which otherwise co-bounds the K = 384 GEMMs and the LayerNorms.
+        total = nq + nr
+        chunk = self.chunk_images(P) if self.dt == DT_BF16 else total
+        flat = [g.reshape(-1, *g.shape[-3:]) for g in groups]
+        sizes = [int(f.shape[0]) for f in flat]
+        for i0 in range(0, total, chunk):
+            i1 = min(total, i0 + chunk)
+            parts, base = [], 0
+            for f, n in zip(flat, sizes):  # slices of the (query..., refs...) image list that fall into [i0, i1)
+                lo, hi = max(i0, base), min(i1, base + n)
+                if lo < hi:
+                    parts.append(f[lo - base:hi - base])
+                base += n
+            h, d, I, _ = self.backbone(parts, st)
+            q_here = max(0, min(i1, nq) - i0)                      # query images in this chunk (they come first)
+            xq_dst = xq32[i0 * P:] if q_here else None
+            mem_dst = mem[max(i0, nq) * P - nq * P:] if (mem is not None and i1 > nq) else None
+            with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + (es if d is not None else 0) + es)):
+                call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS,
+                     _ptr(pe), _ptr(xq_dst), None, _ptr(mem_dst), I, q_here, P, self.dt, st)
         return xq32, mem
+
+    def chunk_images(self, P: int) -> int:
+        """Images per backbone chunk (bf16 mode).  XS_CHUNK_IMAGES overrides (0 = no chunking)."""
+        env = os.environ.get("XS_CHUNK_IMAGES")
+        if env is not None:
+            n = int(env)
+            return n if n > 0 else 1 << 30
+        return 1 << 30
 
     def project_kv(self, mem, st, out=None):
         """K/V of both decoder layers for reference tokens mem (rows, C) -> (rows, 4E)."""
         rows = mem.shape[0]
-        kv = out if out is not None else self._buf("kv", (rows, 4 * self.w.E), self.adtype)
+        kv = out if out is not None else self._buf("kv", (rows, 4 * self.w.E), self.qdtype)
         self._gemm(mem, self.w.kv_w, self.w.kv_b, kv, ACT_NONE, st, tag="gemm_dec_kv", n_real=4 * C)
         return kv
 
@@ -361,8 +409,8 @@ class Engine:
         w, A, E, slot = self.w, self.adtype, self.w.E, self.w.slot
         R = B * P
         f32 = torch.float32
-        qkv_s = self._buf("dec_qkv", (R, 3 * E), A)
-        qc = self._buf("dec_q", (R, E), A)
+        qkv_s = self._buf("dec_qkv", (R, 3 * E), self.qdtype)
+        qc = self._buf("dec_q", (R, E), self.qdtype)
         att = self._buf("dec_att", (R, C), f32)
         d = self._buf("dec_d", (R, C), f32)
         f = self._buf("dec_f", (R, C), f32)
@@ -395,7 +443,7 @@ class Engine:
             with self._op("attn_probs", 0.0, probs.numel() * 4.0):
                 call("xs_attn_probs_one_head", _ptr(qc), _ptr(kv[:, l * 2 * E:]), _ptr(lse), _ptr(probs), B, DEC_HEADS,
                      head_id, P, M, DEC_D, slot, E, P * E, 4 * E, 0 if kv_shared else M * 4 * E,
-                     1.0 / math.sqrt(DEC_D), self.dt, st)
+                     self.attn_scale(DEC_D), self.attn_dt, st)
         self._gemm(xq32, w.h0_w, w.h0_b, f, ACT_LEAKY, st, tag="gemm_dec")
         score = torch.empty(B, PATCH * ph, PATCH * pw, device=self.device, dtype=f32)
         # K12 algorithmic bytes: token features in + fp32 score map out
@@ -409,6 +457,10 @@ class Engine:
     @property
     def kv_width(self):
         return 4 * self.w.E
+
+    @property
+    def kv_dtype(self):
+        return self.qdtype
 
     def cross_attn_partial(self, layer, qc, kv_local, B, P, M_local, packed, st):
         """Cross-attention of decoder layer `layer` over THIS rank's keys only.  packed (fp32, 1-D) receives the

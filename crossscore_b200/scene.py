@@ -83,7 +83,7 @@ class SceneScorer:
         ph, pw = H // PATCH, W // PATCH
         P = ph * pw
         eng, st = self.engine, _stream(self.device)
-        kv = torch.empty(N * P, eng.kv_width, device=self.device, dtype=eng.adtype)
+        kv = torch.empty(N * P, eng.kv_width, device=self.device, dtype=getattr(eng, "kv_dtype", eng.adtype))
         lo, hi = shard_range(N, self.world, self.rank)
         if hi > lo:
             _, mem = eng.features(None, ref_imgs[lo:hi].contiguous(), st)

@@ -39,6 +39,9 @@ extern "C" {
 #define XS_DTYPE_BF16 0
 #define XS_DTYPE_F32 1
 #define XS_DTYPE_TF32 2 /* GEMM operand mode only: fp32 in memory, multiplied as TF32 on the tensor cores */
+#define XS_DTYPE_F16 3  /* attention operands (q, k, v) in fp16: xs_gemm_bias_act out_dtype, xs_flash_attn /
+                           xs_attn_probs_one_head dtype.  The fp16 attention kernel keeps its logits in fp16 tensor-core
+                           accumulators, as the reference's 16-mixed autocast path does (config/default_predict.yaml:25) */
 
 #define XS_ACT_NONE 0
 #define XS_ACT_GELU 1  /* exact (erf) GELU: Dinov2MLP, $SP/transformers/models/dinov2/modeling_dinov2.py:312-328 */
@@ -102,7 +105,8 @@ int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float
 /* K5,K7  h[M,N] += A[M,K] @ W[N,K]^T + bias[N]   (fp32 residual stream updated in place)
  *     Dinov2Layer's `layer_scale(attention_output) + hidden_states` and `layer_scale2(mlp(...)) + hidden_states`
  *     ($SP/transformers/models/dinov2/modeling_dinov2.py:367-386) with LayerScale folded into W / bias: the add is
- *     performed by the epilogue's TMA reduce-store, so the delta never round-trips through HBM (nor through bf16).
+ *     performed in the GEMM epilogue (the residual tile is prefetched by TMA while the tile's MMAs run), so the delta
+ *     never round-trips through HBM (nor through bf16).
  *     dtype = XS_DTYPE_BF16 only; N multiple of 192; every element of h receives exactly one add (deterministic). */
 int xs_gemm_bias_residual(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
                           int M, int N, int K, int dtype, xs_stream_t stream);

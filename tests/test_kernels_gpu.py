@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from crossscore_b200 import _lib
-from crossscore_b200._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, DT_TF32, call
+from crossscore_b200._lib import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F16, DT_F32, DT_TF32, call
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -172,20 +172,22 @@ def attn_ref(q, k, v, scale):
     return torch.softmax(s, -1) @ v, lse
 
 
-def run_attn(dtype_flag, B, H, Lq, Lk, d, slot, nsplit=1, kv_shared=False, seed=0, qscale=1.0, force_f32_out=False):
-    adt = torch.bfloat16 if dtype_flag == DT_BF16 else torch.float32
+def run_attn(dtype_flag, B, H, Lq, Lk, d, slot, nsplit=1, kv_shared=False, seed=0, qscale=1.0, force_f32_out=False,
+             scale=None):
+    adt = {DT_BF16: torch.bfloat16, DT_F16: torch.float16, DT_F32: torch.float32}[dtype_flag]
     Bkv = 1 if kv_shared else B
     q = rnd(B, Lq, H * slot, seed=seed, scale=qscale, dtype=adt)
     k = rnd(Bkv, Lk, H * slot, seed=seed + 1, dtype=adt)
     v = rnd(Bkv, Lk, H * slot, seed=seed + 2, dtype=adt)
-    scale = 1.0 / math.sqrt(d)
+    scale = 1.0 / math.sqrt(d) if scale is None else scale
     o_f32 = 1 if (dtype_flag == DT_F32 or nsplit > 1 or force_f32_out) else 0
-    o = torch.full((nsplit, B * Lq, H * d), float("nan"), device=DEV, dtype=torch.float32 if o_f32 else adt)
+    odt = torch.bfloat16 if dtype_flag == DT_F16 else adt  # the fp16 kernel still emits bf16 (GEMM A operand) or fp32
+    o = torch.full((nsplit, B * Lq, H * d), float("nan"), device=DEV, dtype=torch.float32 if o_f32 else odt)
     lse = torch.full((nsplit, B, H, Lq), float("nan"), device=DEV)
     call("xs_flash_attn", P(q), P(k), P(v), P(o), P(lse), B, H, Lq, Lk, d, slot, H * slot, Lq * H * slot, H * slot,
          Lk * H * slot, int(kv_shared), nsplit, o_f32, scale, dtype_flag, st())
     if nsplit > 1:
-        mdt = torch.float32 if force_f32_out else adt
+        mdt = torch.float32 if force_f32_out else odt
         merged = torch.empty(B * Lq, H * d, device=DEV, dtype=mdt)
         lse_m = torch.empty(B, H, Lq, device=DEV)
         call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d, 0, 0,
@@ -231,6 +233,51 @@ def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale):
     assert err.max() < 0.03, f"max err {err.max().item()}"
     assert err.mean() < 3e-3
     assert (lse - lse_ref).abs().max() < 0.02
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d,nsplit,shared,qscale,folded", [
+    (1, 1, 128, 128, 64, 1, False, 1.0, True),     # single tile
+    (1, 2, 128, 256, 64, 1, False, 1.0, True),     # two kv blocks
+    (1, 2, 128, 192, 64, 1, False, 1.0, True),     # odd number of kv blocks (register buffers swap roles)
+    (2, 6, 1370, 1370, 64, 1, False, 1.0, True),   # DINOv2 shape, ragged tails (odd tail: 1370 = 21*64 + 26)
+    (2, 6, 1370, 1370, 64, 1, False, 1.0, False),  # general scale (HFMA2 with a rounded scale)
+    (1, 8, 128, 128, 48, 1, False, 1.0, True),     # d=48 single tile
+    (2, 8, 1369, 1369, 48, 1, False, 2.0, True),   # decoder self-attention, odd tail (1369 = 21*64 + 25)
+    (1, 8, 300, 6845, 48, 1, False, 3.0, True),    # cross-attention, long kv, peaky softmax (rescale path)
+    (1, 8, 300, 6845, 48, 4, False, 1.0, True),    # split-KV + merge
+    (3, 8, 200, 700, 48, 1, True, 1.0, True),      # shared reference K/V
+    (1, 6, 257, 5000, 64, 1, False, 6.0, True),    # very peaky rows: P overflow detector / fp16 range
+])
+def test_flash_attn_f16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale, folded):
+    """fp16 operands, fp16 logit accumulators, packed-half softmax.  `folded`: the caller pre-multiplied q by
+    scale*log2(e) (here: plain scale = ln 2 on the given q, i.e. logits are log2-domain), so scale_log2 == 1."""
+    scale = math.log(2.0) if folded else None
+    o, ref, lse, lse_ref = run_attn(DT_F16, B, H, Lq, Lk, d, 64, nsplit, shared, qscale=qscale * (0.35 if folded else 1.0),
+                                    scale=scale)
+    assert torch.isfinite(o).all()
+    err = (o - ref).abs()
+    assert err.max() < 0.03, f"max err {err.max().item()}"
+    assert err.mean() < 3e-3
+    assert (lse - lse_ref).abs().max() < 0.02
+
+
+def test_gemm_f16_out():
+    """fp16 GEMM outputs (q|k|v operands of the fp16 attention kernel): bf16 x bf16 and tf32 x tf32 inputs."""
+    for M, N, K in [(1000, 1152, 384), (40000, 1152, 384), (5000, 2048, 384)]:
+        A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+        W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+        b = rnd(N, seed=3)
+        out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+        call("xs_gemm_bias_act", P(A), K, P(W), K, P(b), P(out), N, M, N, K, ACT_NONE, DT_BF16, DT_F16, st())
+        torch.cuda.synchronize()
+        ref = A.float() @ W.float().T + b
+        assert ((out.float() - ref).abs() <= 2e-3 + 1e-3 * ref.abs()).all()
+    A, W, b = rnd(1369, 384, seed=1), rnd(1536, 384, seed=2, scale=0.05), rnd(1536, seed=3)
+    out = torch.full((1369, 1536), float("nan"), device=DEV, dtype=torch.float16)
+    call("xs_gemm_bias_act", P(A), 384, P(W), 384, P(b), P(out), 1536, 1369, 1536, 384, ACT_NONE, DT_TF32, DT_F16, st())
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().T + b.double()
+    assert ((out.double() - ref).abs() <= 8e-3 + 2e-3 * ref.abs()).all()
 
 
 @pytest.mark.parametrize("nsplit", [1, 2])
@@ -361,9 +408,9 @@ def test_head_score_jigsaw(dt, use_tanh, power):
     assert (score.double() - ref).abs().max() < tol
 
 
-@pytest.mark.parametrize("dt", [DT_F32, DT_BF16])
+@pytest.mark.parametrize("dt", [DT_F32, DT_BF16, DT_F16])
 def test_attn_probs_one_head(dt):
-    adt = torch.float32 if dt == DT_F32 else torch.bfloat16
+    adt = {DT_F32: torch.float32, DT_BF16: torch.bfloat16, DT_F16: torch.float16}[dt]
     B, H, Lq, Lk, d = 2, 8, 50, 120, 48
     slot = 48 if dt == DT_F32 else 64
     q, k = rnd(B, Lq, H * slot, seed=1, dtype=adt), rnd(B, Lk, H * slot, seed=2, dtype=adt)

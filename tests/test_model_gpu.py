@@ -111,3 +111,31 @@ def test_errors():
         net(q.to(DEV), r.to(DEV)[:, :, :, :56], False, 0, False)
     with pytest.raises(IndexError):
         net(q.to(DEV), r.to(DEV), True, 8, False)
+
+
+@pytest.mark.parametrize("fuse", ["0", "1"])
+@pytest.mark.parametrize("chunk", ["1", "3", "5"])
+def test_chunked_backbone_matches_unchunked(chunk, fuse, monkeypatch):
+    """The backbone may run a few images at a time (L2-resident intermediates) and with the residual add in the
+    GEMM epilogue or in the LayerNorm kernel: every plan gives the same score map (queries and references
+    straddle chunk boundaries: 2 queries + 2x3 references = 8 images)."""
+    sd = make_state_dict(3)
+    q, r = make_inputs(2, 3, 112, 84, seed=5)
+    q, r = q.to(DEV), r.to(DEV)
+
+    def run():
+        net = CrossScoreNet(default_cfg(), precision="bf16")
+        net.load_state_dict(sd)
+        net = net.to(DEV).eval()
+        out = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+        torch.cuda.synchronize()
+        return out
+
+    monkeypatch.setenv("XS_CHUNK_IMAGES", "0")
+    monkeypatch.setenv("XS_FUSE_RESIDUAL", "0")
+    base = run()
+    monkeypatch.setenv("XS_CHUNK_IMAGES", chunk)
+    monkeypatch.setenv("XS_FUSE_RESIDUAL", fuse)
+    got = run()
+    tol = 1e-6 if fuse == "0" else 5e-3  # the fused plan does not round the residual delta to bf16
+    assert (got - base).abs().max().item() <= tol

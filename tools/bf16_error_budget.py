@@ -33,10 +33,18 @@ def run(sd, q, r, active, dt=torch.float32):
         bqkv = torch.cat([g(p + f"attention.attention.{n}.bias") for n in ("query", "key", "value")], 0)
         qkv = R(y @ wqkv.T + bqkv, "qkv")
         qq, kk, vv = [t.view(I, T, 6, 64).transpose(1, 2) for t in qkv.split(384, -1)]
-        s = qq @ kk.transpose(-1, -2) / 8
+        s = qq @ kk.transpose(-1, -2)
+        if "s16" in active:  # fp16 logit accumulators (tcgen05 D format f16)
+            s = s.half().to(dt)
+        s = s / 8
         s = s - s.max(-1, keepdim=True).values
-        e = torch.exp(s)
-        a = (R(e, "p") @ vv) / e.sum(-1, keepdim=True)
+        if "x16" in active:  # fp16 softmax argument with a stale reference max (8 octaves low) and fp16 P
+            x = ((s * 1.4426950408889634 + 8.0).half()).to(dt)
+            e = torch.exp2(x).half().to(dt)
+            a = (e @ vv) / e.sum(-1, keepdim=True)
+        else:
+            e = torch.exp(s)
+            a = (R(e, "p") @ vv) / e.sum(-1, keepdim=True)
         a = R(a.transpose(1, 2).reshape(I, T, 384), "att")
         d = R(a @ R(g(p + "attention.output.dense.weight") * lam1[:, None], "w").T + g(p + "attention.output.dense.bias") * lam1, "d")
         h = h + d
@@ -58,10 +66,18 @@ def run(sd, q, r, active, dt=torch.float32):
             vh = R(kvsrc @ R(w_in[768:], "w").T + b_in[768:], tagkv)
             Lq, Lk = qh.shape[1], kh.shape[1]
             qh, kh, vh = [t.view(B, -1, 8, 48).transpose(1, 2) for t in (qh, kh, vh)]
-            s = qh @ kh.transpose(-1, -2) / math.sqrt(48)
+            s = qh @ kh.transpose(-1, -2)
+            if "s16" in active:
+                s = s.half().to(dt)
+            s = s / math.sqrt(48)
             s = s - s.max(-1, keepdim=True).values
-            e = torch.exp(s)
-            a = (R(e, "dp") @ vh) / e.sum(-1, keepdim=True)
+            if "x16" in active:
+                x = ((s * 1.4426950408889634 + 8.0).half()).to(dt)
+                e = torch.exp2(x).half().to(dt)
+                a = (e @ vh) / e.sum(-1, keepdim=True)
+            else:
+                e = torch.exp(s)
+                a = (R(e, "dp") @ vh) / e.sum(-1, keepdim=True)
             a = R(a.transpose(1, 2).reshape(B, Lq, 384), "datt")
             return R(a @ gw(pre + "out_proj.weight").T + g(pre + "out_proj.bias"), "dd")
         x32 = O.layer_norm(x32 + mha(x32, R(x32, "x"), p + "self_attn.", "dqkv"), g(p + "norm1.weight"), g(p + "norm1.bias"), 1e-5)
@@ -83,6 +99,14 @@ if __name__ == "__main__":
     def err(active):
         d = (run(sd, q, r, set(active)).double() - base).abs()
         return d.max().item(), d.mean().item()
+    if len(sys.argv) > 1 and sys.argv[1] == "f16":
+        print("all             ", err(ALL))
+        print("all + s16       ", err(ALL + ["s16"]))
+        print("all + s16 + x16 ", err(ALL + ["s16", "x16"]))
+        print("only s16        ", err(["s16"]))
+        print("only s16 + x16  ", err(["s16", "x16"]))
+        print("only p          ", err(["p", "dp"]))
+        sys.exit(0)
     print("none      ", err([]))
     print("all       ", err(ALL))
     for t in ALL:
