@@ -363,59 +363,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           pending_sb = -1;
         }
       };
-      // One packed load brings a whole 64-key block (32 registers); the next block's load is in flight during the
-      // current block's exponentials (S is triple-buffered).
-      uint32_t va[32], vb[32];
+      // Software pipeline as in the fp32 variant, on packed registers: a block is two 32-key chunks of 16 registers;
+      // chunk B's load is in flight during chunk A's exponentials, the next block's chunk A during chunk B's.
+      uint32_t va[16], vb[16];
       if (lane == 0) mbar_wait(s_full + (g0 % ATT_NS), (g0 / ATT_NS) & 1);
       __syncwarp();
       tc_fence_after();
-      tmem_ld32_pack16(tmem_base + lane_off + (g0 % ATT_NS) * 64, va);
+      tmem_ld16_pack16(tmem_base + lane_off + (g0 % ATT_NS) * 64, va);
       pc.lap(0);
 
-      auto block = [&](const int j, uint32_t (&cur)[32], uint32_t (&nxt)[32], auto mask_tag) __attribute__((always_inline)) {
+      auto block = [&](const int j, auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
         const uint32_t g = g0 + j;
         const uint32_t sb = g % ATT_NS;
         const uint32_t t_s = tmem_base + lane_off + sb * 64;
-        tmem_ld_wait32(cur);
+        uint32_t pka[16], pkb[16];
+        uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;  // packed-half partial row sums
+        const uint32_t negm = h2_bcast(-m);
+        // keys >= tail_valid of the last block are past the sequence end: -inf (fp16 0xFC00)
+        auto mask16 = [&](uint32_t (&v)[16], int valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (2 * i >= valid) v[i] = 0xFC00FC00u;
+            else if (2 * i + 1 >= valid) v[i] = (v[i] & 0x0000FFFFu) | 0xFC000000u;
+          }
+        };
+        auto exp16 = [&](const uint32_t (&v)[16], uint32_t nm, uint32_t (&pk)[16]) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            pk[i] = h2_ex2(h2_fma(v[i], sl2h, nm)); a0 = h2_add(a0, pk[i]);
+            pk[i + 1] = h2_ex2(h2_fma(v[i + 1], sl2h, nm)); a1 = h2_add(a1, pk[i + 1]);
+            pk[i + 2] = h2_ex2(h2_fma(v[i + 2], sl2h, nm)); a2 = h2_add(a2, pk[i + 2]);
+            pk[i + 3] = h2_ex2(h2_fma(v[i + 3], sl2h, nm)); a3 = h2_add(a3, pk[i + 3]);
+          }
+        };
+
+        tmem_ld_wait16(va);
+        tmem_ld16_pack16(t_s + 32, vb);  // in flight during chunk A
         pc.lap(1);
-        if (j + 1 < nkv) {
+        if constexpr (MASK) mask16(va, tail_valid);
+        if (j > 0) exp16(va, negm, pka);
+        flush_pending();  // previous block's P
+        pc.lap(2);
+        tmem_ld_wait16(vb);
+        pc.lap(1);
+        // P_g (64 halves = 32 columns) overwrites the upper half of S_sb, all of which is in registers by now
+        if (j > 0) tmem_st16(t_s + 32, pka);
+        pc.lap(3);
+        if (j + 1 < nkv) {  // prefetch chunk A of the next block
           const uint32_t sn = (g + 1) % ATT_NS;
           if (lane == 0) mbar_wait(s_full + (sn), ((g + 1) / ATT_NS) & 1);
           __syncwarp();
+          pc.lap(0);  // pure wait for S_{g+1}
           tc_fence_after();
-          tmem_ld32_pack16(tmem_base + lane_off + sn * 64, nxt);
+          tmem_ld16_pack16(tmem_base + lane_off + sn * 64, va);
         }
-        pc.lap(0);
-        if constexpr (MASK) {  // keys >= tail_valid are past the sequence end: -inf (fp16 0xFC00)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (2 * i >= tail_valid) cur[i] = 0xFC00FC00u;
-            else if (2 * i + 1 >= tail_valid) cur[i] = (cur[i] & 0x0000FFFFu) | 0xFC000000u;
-          }
-        }
-        uint32_t pk[32];
-        uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;  // packed-half partial row sums (8 pairs each)
-        const uint32_t negm = h2_bcast(-m);
-        if (j > 0) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            pk[i] = h2_ex2(h2_fma(cur[i], sl2h, negm)); a0 = h2_add(a0, pk[i]);
-            pk[i + 1] = h2_ex2(h2_fma(cur[i + 1], sl2h, negm)); a1 = h2_add(a1, pk[i + 1]);
-            pk[i + 2] = h2_ex2(h2_fma(cur[i + 2], sl2h, negm)); a2 = h2_add(a2, pk[i + 2]);
-            pk[i + 3] = h2_ex2(h2_fma(cur[i + 3], sl2h, negm)); a3 = h2_add(a3, pk[i + 3]);
-          }
-        }
-        flush_pending();  // previous block's P: its tcgen05.st has long landed
-        if (j > 0) {
-#pragma unroll
-          for (int i = 16; i < 32; i += 4) {
-            pk[i] = h2_ex2(h2_fma(cur[i], sl2h, negm)); a0 = h2_add(a0, pk[i]);
-            pk[i + 1] = h2_ex2(h2_fma(cur[i + 1], sl2h, negm)); a1 = h2_add(a1, pk[i + 1]);
-            pk[i + 2] = h2_ex2(h2_fma(cur[i + 2], sl2h, negm)); a2 = h2_add(a2, pk[i + 2]);
-            pk[i + 3] = h2_ex2(h2_fma(cur[i + 3], sl2h, negm)); a3 = h2_add(a3, pk[i + 3]);
-          }
-        }
+        pc.lap(6);  // fence + load issue
+        if constexpr (MASK) mask16(vb, tail_valid - 32);
+        if (j > 0) exp16(vb, negm, pkb);
         uint32_t at = h2_add(h2_add(a0, a1), h2_add(a2, a3));
         float bsum = h2_lo(at) + h2_hi(at);
         // Stale reference max, as in the fp32 variant: the block's row sum is the overflow detector (a P beyond
@@ -423,9 +428,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const bool need = (j == 0) || !(bsum <= ATT_SUM_LIMIT_F16);
         if (__any_sync(0xffffffffu, need)) {
           pc.lap(2);
-          uint32_t mx2 = cur[0];
+          if (j + 1 < nkv) tmem_ld_wait16(va);  // the prefetch must land before va is reused
+          tmem_ld16_pack16(t_s, va);            // S chunk A again (columns 0..31 have not been overwritten)
+          tmem_ld_wait16(va);
+          if constexpr (MASK) mask16(va, tail_valid);
+          uint32_t mx2 = h2_max(va[0], vb[0]);
 #pragma unroll
-          for (int i = 1; i < 32; ++i) mx2 = h2_max(mx2, cur[i]);
+          for (int i = 1; i < 16; ++i) mx2 = h2_max(mx2, h2_max(va[i], vb[i]));
           const float mx = fmaxf(h2_lo(mx2), h2_hi(mx2)) * sl2;
           float m_new = need ? fmaxf(mx, m) : m;
           m_new = h2_lo(h2_bcast(m_new));  // keep m representable in fp16 (exact when scale_log2 == 1)
@@ -448,36 +457,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           m = m_new;
           const uint32_t negm2 = h2_bcast(-m);
           a0 = a1 = a2 = a3 = 0u;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            pk[i] = h2_ex2(h2_fma(cur[i], sl2h, negm2)); a0 = h2_add(a0, pk[i]);
-            pk[i + 1] = h2_ex2(h2_fma(cur[i + 1], sl2h, negm2)); a1 = h2_add(a1, pk[i + 1]);
-            pk[i + 2] = h2_ex2(h2_fma(cur[i + 2], sl2h, negm2)); a2 = h2_add(a2, pk[i + 2]);
-            pk[i + 3] = h2_ex2(h2_fma(cur[i + 3], sl2h, negm2)); a3 = h2_add(a3, pk[i + 3]);
-          }
+          tc_wait_st();  // the early store of the stale P_A must not pass the corrected one
+          exp16(va, negm2, pka);
+          tmem_st16(t_s + 32, pka);
+          exp16(vb, negm2, pkb);
           at = h2_add(h2_add(a0, a1), h2_add(a2, a3));
           bsum = h2_lo(at) + h2_hi(at);
+          if (j + 1 < nkv) tmem_ld16_pack16(tmem_base + lane_off + ((g + 1) % ATT_NS) * 64, va);  // redo the prefetch
           pc.lap(7);
         }
         l += bsum;
         pc.lap(2);
-        tmem_st32(t_s + 32, pk);  // P_g (64 halves) over the upper half of S_sb, whose logits are all in registers
+        tmem_st16(t_s + 48, pkb);
         pending_sb = static_cast<int>(sb);
         pc.lap(3);
       };
-      {
-        int j = 0;
-        for (; j + 2 < nkv; j += 2) {
-          block(j, va, vb, MaskNo{});
-          block(j + 1, vb, va, MaskNo{});
-        }
-        if (j + 2 == nkv) {
-          block(j, va, vb, MaskNo{});
-          block(j + 1, vb, va, MaskYes{});
-        } else {
-          block(j, va, vb, MaskYes{});
-        }
-      }
+      for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
+      block(nkv - 1, MaskYes{});
       flush_pending();
       g0 += nkv;
 
@@ -486,11 +482,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       pc.lap(4);
       tc_fence_after();
-      tmem_ld32(t_o, va);
-      if constexpr (DV == 64) tmem_ld32(t_o + 32, vb);
-      else tmem_ld16_lo(t_o + 32, vb);
-      tmem_ld_wait32(va);
-      tmem_ld_wait32(vb);
+      uint32_t oa[32], ob[32];
+      tmem_ld32(t_o, oa);
+      if constexpr (DV == 64) tmem_ld32(t_o + 32, ob);
+      else tmem_ld16_lo(t_o + 32, ob);
+      tmem_ld_wait32(oa);
+      tmem_ld_wait32(ob);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
@@ -503,12 +500,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (row_g < p.Lq) {
         if (p.o_is_f32) {
           float* dst = reinterpret_cast<float*>(p.o) + o_off;
-          store_row_f32<0, 32>(dst, va, inv);
-          store_row_f32<0, DV - 32>(dst + 32, vb, inv);
+          store_row_f32<0, 32>(dst, oa, inv);
+          store_row_f32<0, DV - 32>(dst + 32, ob, inv);
         } else {
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.o) + o_off;
-          store_row_bf16<0, 32>(dst, va, inv);
-          store_row_bf16<0, DV - 32>(dst + 32, vb, inv);
+          store_row_bf16<0, 32>(dst, oa, inv);
+          store_row_bf16<0, DV - 32>(dst + 32, ob, inv);
         }
         if (p.lse != nullptr) {
           p.lse[static_cast<long long>(t.split) * p.lse_split_stride +
@@ -832,10 +829,10 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
       unsigned long long h[48];
       XS_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
       const double ctas = double(p.n_tiles);
-      fprintf(stderr, "attn f16 prof (clk per tile): softmax warp: wait_S+ld_issue %.0f  ld_wait %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
-                      "epi %.0f  slow %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
+      fprintf(stderr, "attn f16 prof (clk per tile): softmax warp: wait_S %.0f  ld_wait %.0f  exp %.0f  st_P %.0f  wait_O %.0f  "
+                      "epi %.0f  fence+ld_issue %.0f  slow %.0f | mma warp: prologue %.0f  wait_P %.0f  issue_PV %.0f  waitK+issue_QK %.0f\n",
               h[0] / ctas / 4, h[1] / ctas / 4, h[2] / ctas / 4, h[3] / ctas / 4, h[4] / ctas / 4, h[5] / ctas / 4,
-              h[7] / ctas / 4, h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
+              h[6] / ctas / 4, h[7] / ctas / 4, h[8] / ctas, h[9] / ctas, h[10] / ctas, h[11] / ctas);
       return 0;
     }
     if (head_dim == 64) {

@@ -173,9 +173,10 @@ class Engine:
         _lib.load()
         with torch.cuda.device(device):
             call("xs_device_check")
-        # bf16 product mode: attention runs on fp16 operands with fp16 logit accumulators (XS_ATTN_F16=0: the bf16 /
-        # fp32-logit kernel, kept for A/B measurements); everything else (GEMM operands, attention output) stays bf16
-        self.attn_f16 = precision == "bf16" and os.environ.get("XS_ATTN_F16", "1") != "0"
+        # XS_ATTN_F16=1 (bf16 product mode only): attention on fp16 operands with fp16 logit accumulators and a
+        # packed-half softmax.  Parity-tested, but measured no faster than the bf16 / fp32-logit kernel (both end up
+        # bound by the MUFU), so it is opt-in.
+        self.attn_f16 = precision == "bf16" and os.environ.get("XS_ATTN_F16", "0") == "1"
         self.w = PackedWeights(sd, device, precision, do_self_attn, fold_qscale=self.attn_f16)
         self.device = device
         self.dt = self.w.dt

@@ -256,9 +256,11 @@ def test_flash_attn_f16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale, folded):
                                     scale=scale)
     assert torch.isfinite(o).all()
     err = (o - ref).abs()
-    assert err.max() < 0.03, f"max err {err.max().item()}"
+    # fp16 logits: an absolute error of |s| * 2^-11 in the exponent; the very peaky case has |s| up to ~60
+    tol = 0.06 if qscale >= 6.0 else 0.03
+    assert err.max() < tol, f"max err {err.max().item()}"
     assert err.mean() < 3e-3
-    assert (lse - lse_ref).abs().max() < 0.02
+    assert (lse - lse_ref).abs().max() < (0.05 if qscale >= 6.0 else 0.02)
 
 
 def test_gemm_f16_out():

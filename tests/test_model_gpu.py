@@ -139,3 +139,19 @@ def test_chunked_backbone_matches_unchunked(chunk, fuse, monkeypatch):
     got = run()
     tol = 1e-6 if fuse == "0" else 5e-3  # the fused plan does not round the residual delta to bf16
     assert (got - base).abs().max().item() <= tol
+
+
+def test_fp16_logit_attention_plan_parity(monkeypatch):
+    """XS_ATTN_F16=1: fp16 q/k/v, fp16 logit accumulators, scale folded into the query projections -- same
+    tolerances against the reference's golden vectors as the default plan."""
+    monkeypatch.setenv("XS_ATTN_F16", "1")
+    for case in ("g2_nonsquare_84x117_n3_attn", "g7_168x154_n1"):
+        rec = load_golden(case)
+        net, q, r = build_net(rec, "bf16")
+        out = net(q, r, bool(rec["need_w"]), int(rec["head_id"]), False)
+        torch.cuda.synchronize()
+        mx, mean = compare_to_golden(out["score_map_ref_cross"], rec)
+        assert mx <= 1e-2 and mean <= 1e-3, f"{case}: max {mx:.3e} mean {mean:.3e}"
+        if rec["need_w"]:
+            d = np.abs(out["attn_weights_map_ref_cross"].float().cpu().numpy() - rec["attn"])
+            assert d.max() <= 2e-3
