@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("XS_LIB_PATH") or os.path.join(HERE, "libcrossscore_sm
 DT_BF16, DT_F32, DT_TF32, DT_F16 = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY = 0, 1, 2, 3
 OP_PATCH_EMBED = 1
+OP_SCORE_POSTPROCESS = 2
 
 _p, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 
@@ -34,6 +35,8 @@ SIGNATURES = {
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_lse_merge": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _i, _p]),
     "xs_head_score_jigsaw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "xs_preprocess_u8_resize_normalize": (_i, [_p, _i, _i, _i, _p, _i, _i, C.POINTER(C.c_float), _p]),
+    "xs_score_postprocess": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _f, _f, _p, _sz, _p]),
     "xs_attn_probs_one_head": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p]),
 }
 

@@ -84,6 +84,10 @@ int head_jigsaw_tc(const void*, int, const void*, int, const float*, float*, int
 int flash_attn_bf16_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long,
                        long long, long long, long long, int, int, int, float, int, cudaStream_t);
 int gemm_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, cudaStream_t);
+int preprocess_u8(const uint8_t*, int, int, int, float*, int, int, const float*, cudaStream_t);
+size_t postprocess_workspace_bytes(int);
+int postprocess_score(const float*, int, int, int, float*, uint16_t*, int, uint8_t*, float, float, void*, size_t,
+                      cudaStream_t);
 int head_jigsaw_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, float,
                     cudaStream_t);
 int flash_attn_f32(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, long long,
@@ -129,6 +133,7 @@ size_t xs_workspace_bytes(int op, int a, int b, int c, int dtype) {
     const size_t P = (size_t)(b / 14) * (size_t)(c / 14);
     return (size_t)a * P * (size_t)kpad_for(dtype) * (size_t)elem_bytes(dtype);
   }
+  if (op == XS_OP_SCORE_POSTPROCESS) return postprocess_workspace_bytes(a);
   return 0;
 }
 
@@ -240,6 +245,18 @@ int xs_head_score_jigsaw(const void* A, int lda, const void* W, int ldw, const f
                            pw, K, use_tanh, power, st);
   set_last_error("head_score_jigsaw: unknown dtype %d", dtype);
   return -1;
+}
+
+int xs_preprocess_u8_resize_normalize(const uint8_t* img, int n, int H0, int W0, float* out, int H1, int W1,
+                                      const float* mean_std, xs_stream_t stream) {
+  return preprocess_u8(img, n, H0, W0, out, H1, W1, mean_std, static_cast<cudaStream_t>(stream));
+}
+
+int xs_score_postprocess(const float* score, int B, int H, int W, float* frame_mean, uint16_t* gray16, int vrange_mode,
+                         uint8_t* rgb, float vmin, float vmax, void* workspace, size_t workspace_bytes,
+                         xs_stream_t stream) {
+  return postprocess_score(score, B, H, W, frame_mean, gray16, vrange_mode, rgb, vmin, vmax, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int xs_attn_probs_one_head(const void* q, const void* k, const float* lse, float* probs, int B, int heads, int head,

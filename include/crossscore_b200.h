@@ -49,6 +49,7 @@ extern "C" {
 #define XS_ACT_LEAKY 3 /* head LeakyReLU(0.01): model/cross_reference.py:47 */
 
 #define XS_OP_PATCH_EMBED 1
+#define XS_OP_SCORE_POSTPROCESS 2 /* xs_workspace_bytes(op, B, 0, 0, 0) */
 
 typedef void* xs_stream_t; /* cudaStream_t */
 
@@ -56,7 +57,7 @@ int xs_version(void);
 const char* xs_last_error(void);
 /* 0 if the current device is compute capability 10.x (B200), <0 otherwise */
 int xs_device_check(void);
-/* scratch bytes an operator needs; XS_OP_PATCH_EMBED: (n_images, H, W) */
+/* scratch bytes an operator needs; XS_OP_PATCH_EMBED: (n_images, H, W); XS_OP_SCORE_POSTPROCESS: (B) */
 size_t xs_workspace_bytes(int op, int a, int b, int c, int dtype);
 
 /* K1  Dinov2PatchEmbeddings.projection: Conv2d(3,384,k=14,s=14) == im2col + GEMM
@@ -145,6 +146,28 @@ int xs_attn_probs_one_head(const void* q, const void* k, const float* lse, float
                            int head, int Lq, int Lk, int head_dim, int head_slot, long long q_row_stride,
                            long long q_batch_stride, long long kv_row_stride, long long kv_batch_stride,
                            float scale, int dtype, xs_stream_t stream);
+
+/* ---- the steps either side of the path ---------------------------------- */
+
+/* F2  uint8 HWC image(s) -> /255 -> antialiased bilinear resize -> ImageNet normalise -> fp32 NCHW: the dataloader's
+ *     per-image CPU work (utils/io/images.py:14-29 image_read/f32; dataloading/dataset/nvs_dataset.py:218-225
+ *     resize_all = torchvision T.Resize(short side, BILINEAR, antialias=True), task/predict.py:87-92;
+ *     T.Normalize, task/predict.py:69-74) done on the device in front of xs_patch_embed.
+ *     img (n, H0, W0, 3) uint8, out (n, 3, H1, W1) fp32; the caller computes (H1, W1) with torchvision's rule
+ *     (short side -> size, long side -> int(size * long / short)); H1 == H0 && W1 == W0 skips the filter.
+ *     mean_std: 6 floats in HOST memory (mean rgb, std rgb).  Down-scaling factors up to 10. */
+int xs_preprocess_u8_resize_normalize(const uint8_t* img, int n, int H0, int W0, float* out, int H1, int W1,
+                                      const float* mean_std, xs_stream_t stream);
+
+/* F3  score map (B, H, W) fp32 -> any of: per-frame mean (utils/io/score_summariser.py:180-181), uint16 gray
+ *     quantisation (utils/io/images.py:49-63 metric_map_write; vrange_mode 0: [0,1] -> m*65535, 1: [-1,1] ->
+ *     (m+1)*32767, truncated), turbo RGB (B, H, W, 3) uint8 (utils/misc/image.py:35-49 gray2rgb with vrange
+ *     (vmin, vmax)); the products utils/io/batch_writer.py:114-135,263-270 writes.  Outputs may be NULL.
+ *     workspace: xs_workspace_bytes(XS_OP_SCORE_POSTPROCESS, B, 0, 0, 0) bytes when frame_mean is requested (the mean
+ *     is a fixed-order fp64 reduction: deterministic). */
+int xs_score_postprocess(const float* score, int B, int H, int W, float* frame_mean, uint16_t* gray16, int vrange_mode,
+                         uint8_t* rgb, float vmin, float vmax, void* workspace, size_t workspace_bytes,
+                         xs_stream_t stream);
 
 #ifdef __cplusplus
 }

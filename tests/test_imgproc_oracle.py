@@ -60,3 +60,12 @@ def test_frame_mean():
     rng = np.random.default_rng(1)
     s = rng.random((3, 28, 42), dtype=np.float32)
     assert np.allclose(IO.frame_mean(s), s.mean(axis=(1, 2)), rtol=1e-6)
+
+
+def test_cuda_turbo_lut_header_matches_table():
+    """crossscore_b200/csrc/xs_turbo.h (what the kernel indexes) == floor(255 * table) (what gray2rgb + u8 give)."""
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "crossscore_b200", "csrc", "xs_turbo.h")
+    body = open(path).read().split("{", 2)[2].split("}")[0]
+    vals = np.array([int(v) for v in re.findall(r"\d+", body)], dtype=np.uint8).reshape(256, 3)
+    assert np.array_equal(vals, (IO.turbo_table() * 255.0).astype(np.uint8))
