@@ -31,6 +31,8 @@ struct ResizeParams {
   float scale_y, scale_x;  // in / out (fp32 division, as ATen's area_pixel_compute_scale)
   float mean[3], std[3];
   int in_rows_max, in_cols_max;  // bound of the input window of a tile (host-computed, sizes the shared memory)
+  int raw_pitch;                 // bytes per staged row (multiple of 4)
+  long long total_bytes;         // n * H0 * W0 * 3
 };
 
 // first input index and tap count of output index i (ATen _compute_indices_min_size_weights_aa, align_corners=False)
@@ -59,7 +61,7 @@ __device__ __forceinline__ void aa_weights(int xmin, int xsize, float center, fl
 __global__ void __launch_bounds__(RS_THREADS) resize_aa_norm_kernel(ResizeParams p) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
   // layout: wx[RS_TW][MAXTAP] | wy[RS_TH][MAXTAP] | x0[RS_TW], nx[RS_TW], y0[RS_TH], ny[RS_TH] | lut[256] |
-  //         tmp[in_rows_max][RS_TW][3] fp32 | raw[in_rows_max][in_cols_max * 3] u8
+  //         rshift[in_rows_max] | tmp[in_rows_max][RS_TW][3] fp32 | raw[in_rows_max][raw_pitch] u8
   float* wx = reinterpret_cast<float*>(rs_smem);
   float* wy = wx + RS_TW * RS_MAXTAP;
   int* x0s = reinterpret_cast<int*>(wy + RS_TH * RS_MAXTAP);
@@ -67,7 +69,8 @@ __global__ void __launch_bounds__(RS_THREADS) resize_aa_norm_kernel(ResizeParams
   int* y0s = nxs + RS_TW;
   int* nys = y0s + RS_TH;
   float* lut = reinterpret_cast<float*>(nys + RS_TH);
-  float* tmp = lut + 256;
+  int* rshift = reinterpret_cast<int*>(lut + 256);  // [in_rows_max] byte offset of the window inside its first word
+  float* tmp = reinterpret_cast<float*>(rshift + p.in_rows_max);
   uint8_t* raw = reinterpret_cast<uint8_t*>(tmp + static_cast<size_t>(p.in_rows_max) * RS_TW * 3);
 
   const int tid = threadIdx.x;
@@ -98,13 +101,31 @@ __global__ void __launch_bounds__(RS_THREADS) resize_aa_norm_kernel(ResizeParams
   const int ylo = y0s[0], yhi = y0s[th - 1] + nys[th - 1];
   const int ncol = xhi - xlo, nrow = yhi - ylo;
   const int row_bytes = ncol * 3;
-  const int raw_pitch = p.in_cols_max * 3;
-  // 1. stage the window (coalesced byte rows)
-  const uint8_t* src = p.img + (static_cast<size_t>(img) * p.H0 + ylo) * p.W0 * 3 + static_cast<size_t>(xlo) * 3;
+  const int raw_pitch = p.raw_pitch;
+  // 1. stage the window: one warp per row, aligned 32-bit words (the window starts `shift` bytes into its first word)
+  const long long off0 = (static_cast<long long>(img) * p.H0 + ylo) * p.W0 * 3 + static_cast<long long>(xlo) * 3;
+  const long long full_words = p.total_bytes >> 2;  // words that lie entirely inside the image buffer
   for (int r = tid >> 5; r < nrow; r += RS_THREADS / 32) {
-    const uint8_t* s = src + static_cast<size_t>(r) * p.W0 * 3;
-    uint8_t* d = raw + r * raw_pitch;
-    for (int b = tid & 31; b < row_bytes; b += 32) d[b] = s[b];
+    const long long off = off0 + static_cast<long long>(r) * p.W0 * 3;
+    const int shift = static_cast<int>(off & 3);
+    const long long w0 = (off - shift) >> 2;
+    const int nwords = (row_bytes + shift + 3) >> 2;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(p.img) + w0;
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(raw + r * raw_pitch);
+    for (int w = tid & 31; w < nwords; w += 32) {
+      uint32_t v;
+      if (w0 + w < full_words) {
+        v = __ldg(s4 + w);
+      } else {  // the last, partial word of the whole buffer: byte loads
+        v = 0;
+        for (int b = 0; b < 4; ++b) {
+          const long long a = ((w0 + w) << 2) + b;
+          if (a < p.total_bytes) v |= static_cast<uint32_t>(p.img[a]) << (8 * b);
+        }
+      }
+      d4[w] = v;
+    }
+    if ((tid & 31) == 0) rshift[r] = shift;
   }
   __syncthreads();
   // 2. width pass: tmp[r][tx][c] = sum_k wx[tx][k] * lut[raw[r][x0 - xlo + k][c]]   (fp32, taps in ascending order)
@@ -112,7 +133,7 @@ __global__ void __launch_bounds__(RS_THREADS) resize_aa_norm_kernel(ResizeParams
     const int r = e / tw, tx = e - r * tw;
     const int xs = x0s[tx] - xlo, n = nxs[tx];
     const float* w = wx + tx * RS_MAXTAP;
-    const uint8_t* rp = raw + r * raw_pitch + xs * 3;
+    const uint8_t* rp = raw + r * raw_pitch + rshift[r] + xs * 3;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int k = 0; k < n; ++k) {
       const float wk = w[k];
@@ -157,6 +178,32 @@ __global__ void __launch_bounds__(256) u8_norm_kernel(const uint8_t* __restrict_
   }
 }
 
+// same-size path, 4 pixels per thread: three aligned words in, one float4 per channel plane out (H*W % 4 == 0)
+__global__ void __launch_bounds__(256) u8_norm_vec4_kernel(const uint32_t* __restrict__ img, float* __restrict__ out,
+                                                           long long n_img, long long hw, float m0, float m1, float m2,
+                                                           float s0, float s1, float s2) {
+  const long long groups = n_img * (hw >> 2);
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long im = g / (hw >> 2);
+    const long long pix = (g - im * (hw >> 2)) << 2;
+    const uint32_t* s = img + (im * hw + pix) * 3 / 4;
+    const uint32_t w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2);
+    const uint8_t b[12] = {uint8_t(w0), uint8_t(w0 >> 8), uint8_t(w0 >> 16), uint8_t(w0 >> 24),
+                           uint8_t(w1), uint8_t(w1 >> 8), uint8_t(w1 >> 16), uint8_t(w1 >> 24),
+                           uint8_t(w2), uint8_t(w2 >> 8), uint8_t(w2 >> 16), uint8_t(w2 >> 24)};
+    auto nrm = [](uint8_t v, float mean, float sd) {
+      return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), mean), sd);
+    };
+    float* o = out + im * 3 * hw + pix;
+    *reinterpret_cast<float4*>(o) = make_float4(nrm(b[0], m0, s0), nrm(b[3], m0, s0), nrm(b[6], m0, s0), nrm(b[9], m0, s0));
+    *reinterpret_cast<float4*>(o + hw) =
+        make_float4(nrm(b[1], m1, s1), nrm(b[4], m1, s1), nrm(b[7], m1, s1), nrm(b[10], m1, s1));
+    *reinterpret_cast<float4*>(o + 2 * hw) =
+        make_float4(nrm(b[2], m2, s2), nrm(b[5], m2, s2), nrm(b[8], m2, s2), nrm(b[11], m2, s2));
+  }
+}
+
 static inline int aa_span(int in_size, int out_size, int tile) {
   // upper bound of the input window of `tile` consecutive output indices
   const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
@@ -169,9 +216,19 @@ int preprocess_u8(const uint8_t* img, int n, int H0, int W0, float* out, int H1,
   XS_CHECK_ARG(n > 0 && H0 > 0 && W0 > 0 && H1 > 0 && W1 > 0, "preprocess: empty problem");
   XS_CHECK_ARG(mean_std != nullptr, "preprocess: mean_std (6 floats, host memory) is required");
   if (H0 == H1 && W0 == W1) {
+    const long long cap = static_cast<long long>(num_sms()) * 32;
+    const long long hw = static_cast<long long>(H0) * W0;
+    if ((hw & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      const long long groups = static_cast<long long>(n) * (hw >> 2);
+      const long long gv = (groups + 255) / 256;
+      u8_norm_vec4_kernel<<<static_cast<int>(gv < cap ? gv : cap), 256, 0, stream>>>(
+          reinterpret_cast<const uint32_t*>(img), out, n, hw, mean_std[0], mean_std[1], mean_std[2], mean_std[3],
+          mean_std[4], mean_std[5]);
+      XS_LAUNCH_CHECK();
+      return 0;
+    }
     const long long total = static_cast<long long>(n) * 3 * H0 * W0;
     long long g = (total + 255) / 256;
-    const long long cap = static_cast<long long>(num_sms()) * 32;
     u8_norm_kernel<<<static_cast<int>(g < cap ? g : cap), 256, 0, stream>>>(img, out, n, H0, W0, mean_std[0], mean_std[1],
                                                                          mean_std[2], mean_std[3], mean_std[4],
                                                                          mean_std[5]);
@@ -197,9 +254,12 @@ int preprocess_u8(const uint8_t* img, int n, int H0, int W0, float* out, int H1,
                smax);
   p.in_rows_max = aa_span(H0, H1, RS_TH);
   p.in_cols_max = aa_span(W0, W1, RS_TW);
+  p.raw_pitch = (p.in_cols_max * 3 + 3 + 3) & ~3;
+  p.total_bytes = static_cast<long long>(n) * H0 * W0 * 3;
+  XS_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 3) == 0, "preprocess: image pointer must be 4-byte aligned");
   const size_t smem = sizeof(float) * (RS_TW * RS_MAXTAP + RS_TH * RS_MAXTAP + 256) + sizeof(int) * 2 * (RS_TW + RS_TH) +
-                     sizeof(float) * static_cast<size_t>(p.in_rows_max) * RS_TW * 3 +
-                     static_cast<size_t>(p.in_rows_max) * p.in_cols_max * 3 + 16;
+                     sizeof(int) * p.in_rows_max + sizeof(float) * static_cast<size_t>(p.in_rows_max) * RS_TW * 3 +
+                     static_cast<size_t>(p.in_rows_max) * p.raw_pitch + 16;
   XS_CHECK_ARG(smem <= 200 * 1024, "preprocess: input window of one tile needs %zu bytes of shared memory", smem);
   XS_CUDA(cudaFuncSetAttribute(resize_aa_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((W1 + RS_TW - 1) / RS_TW, (H1 + RS_TH - 1) / RS_TH, n);

@@ -26,7 +26,8 @@ def test_preprocess_matches_torchvision_golden():
         assert np.abs(got - want).max() <= 2e-6, (k, np.abs(got - want).max())  # fp32: a few ulp of |x| <= 2.7
 
 
-@pytest.mark.parametrize("H,W,size", [(540, 960, 518), (1080, 1920, 518), (518, 518, 518), (300, 200, 518), (777, 1234, 224)])
+@pytest.mark.parametrize("H,W,size", [(540, 960, 518), (1080, 1920, 518), (518, 518, 518), (300, 200, 518), (777, 1234, 224),
+                                      (33, 35, -1), (61, 47, 47), (2160, 3840, 518)])
 def test_preprocess_matches_oracle_batched(H, W, size):
     rng = np.random.default_rng(H + W)
     u8 = rng.integers(0, 256, size=(2, H, W, 3), dtype=np.uint8)
