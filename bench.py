@@ -194,6 +194,29 @@ def run_ours(args):
     e2e_value = world * B * K / (ms_e2e * 1e-3)
     assert bool(torch.isfinite(host_out).all())
 
+    # ---- full chain around the model: uint8 host images -> device preprocessing -> forward
+    #      -> device post-processing -> host frame means + uint16 maps ------------------------------------------
+    from crossscore_b200.runner import HostPipeline
+    g = torch.Generator().manual_seed(200 + rank)
+    q8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+    r8 = torch.randint(0, 256, (B, N_REF, H, W, 3), generator=g, dtype=torch.uint8).pin_memory()
+    pipe = HostPipeline(net, dev)
+    for _ in range(2):
+        pipe.submit(q8, r8)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        means_h, maps_h = pipe.submit(q8, r8)
+    e1.record()
+    barrier()
+    ms_pipe = max_over_ranks(e0.elapsed_time(e1))
+    pipe_value = world * B * K / (ms_pipe * 1e-3)
+    assert bool(torch.isfinite(means_h).all())
+    pipeline = {"value": pipe_value, "unit": "maps/s", "ms_per_step": ms_pipe / K,
+                "h2d_bytes_per_step": pipe.h2d_bytes(q8, r8), "d2h_bytes_per_step": pipe.d2h_bytes(q8),
+                "stages": "uint8 HWC host images -> H2D -> xs_preprocess_u8_resize_normalize -> CrossScoreNet.forward -> "
+                          "xs_score_postprocess (frame mean + uint16 map) -> D2H"}
+
     # ---- per-kernel roofline (instrumented pass, CUDA events on the launching stream) --------------------
     eng = net._engine(dev)
     eng.prof = []
@@ -261,6 +284,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "maps/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": scorer.h2d_bytes(qh, rh), "d2h_bytes_per_step": int(host_out.numel() * 4)},
+        "pipeline": pipeline,
         "gpu_launches": launches,
         "clocks": clocks,
         "model_tflops": value * fpm / 1e12,

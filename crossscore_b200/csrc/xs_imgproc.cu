@@ -262,6 +262,8 @@ int preprocess_u8(const uint8_t* img, int n, int H0, int W0, float* out, int H1,
                      static_cast<size_t>(p.in_rows_max) * p.raw_pitch + 16;
   XS_CHECK_ARG(smem <= 200 * 1024, "preprocess: input window of one tile needs %zu bytes of shared memory", smem);
   XS_CUDA(cudaFuncSetAttribute(resize_aa_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // many small blocks per SM: ask for the largest shared-memory carve-out so that threads, not shared memory, cap occupancy
+  XS_CUDA(cudaFuncSetAttribute(resize_aa_norm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   dim3 grid((W1 + RS_TW - 1) / RS_TW, (H1 + RS_TH - 1) / RS_TH, n);
   resize_aa_norm_kernel<<<grid, RS_THREADS, smem, stream>>>(p);
   XS_LAUNCH_CHECK();

@@ -55,3 +55,68 @@ class HostScorer:
         outs[b].copy_(score, non_blocking=True)
         self._step += 1
         return outs[b]
+
+
+class HostPipeline:
+    """uint8 host images in, frame means + uint16 score maps out: the whole chain of SURVEY.md section 8f around the
+    model on the device (decode excluded).  Per batch: H2D of the uint8 pixels (a quarter of the fp32 bytes the
+    reference's dataloader hands to Lightning) on a copy stream, xs_preprocess_u8_resize_normalize,
+    CrossScoreNet.forward, xs_score_postprocess, D2H of (B,) means and (B,H,W) uint16 maps (half of the fp32 map).
+    Double-buffered like HostScorer."""
+
+    def __init__(self, net, device="cuda:0", resize_short_side: int = -1, gray16_vrange=(0, 1), depth: int = 2):
+        from . import imgproc
+        self.imgproc = imgproc
+        self.net, self.device, self.depth = net, torch.device(device), depth
+        self.resize, self.vrange = resize_short_side, list(gray16_vrange)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._bufs = None
+        self._copied = [torch.cuda.Event() for _ in range(depth)]
+        self._consumed = [torch.cuda.Event() for _ in range(depth)]
+        self._step = 0
+
+    def _ensure(self, q, r):
+        key = (tuple(q.shape), tuple(r.shape))
+        if self._bufs is None or self._bufs[0] != key:
+            dev = self.device
+            qs = [torch.empty(q.shape, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+            rs = [torch.empty(r.shape, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+            B, H0, W0 = q.shape[0], q.shape[1], q.shape[2]
+            H1, W1 = self.imgproc.resize_output_size(H0, W0, self.resize)
+            H, W = 14 * (H1 // 14), 14 * (W1 // 14)
+            means = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(self.depth)]
+            maps = [torch.empty(B, H, W, dtype=torch.uint16).pin_memory() for _ in range(self.depth)]
+            self._bufs = (key, qs, rs, means, maps)
+            self._step = 0
+        return self._bufs[1:]
+
+    def h2d_bytes(self, q, r):
+        return q.numel() + r.numel()
+
+    def d2h_bytes(self, q):
+        _, _, _, means, maps = self._bufs
+        return means[0].numel() * 4 + maps[0].numel() * 2
+
+    def submit(self, q_host: torch.Tensor, r_host: torch.Tensor):
+        """q_host (B,H,W,3), r_host (B,N,H,W,3) pinned uint8.  Returns (means, maps16) pinned host tensors, valid
+        once the current stream has been synchronised (until `depth` later submits)."""
+        qs, rs, means, maps = self._ensure(q_host, r_host)
+        b = self._step % self.depth
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self._step >= self.depth:
+                self.copy_stream.wait_event(self._consumed[b])
+            qs[b].copy_(q_host, non_blocking=True)
+            rs[b].copy_(r_host, non_blocking=True)
+            self._copied[b].record(self.copy_stream)
+        main.wait_event(self._copied[b])
+        B, N = r_host.shape[0], r_host.shape[1]
+        q = self.imgproc.preprocess_u8(qs[b], self.resize)
+        r = self.imgproc.preprocess_u8(rs[b].view(B * N, *r_host.shape[2:]), self.resize)
+        self._consumed[b].record(main)
+        score = self.net(q, r.view(B, N, *r.shape[1:]), False, 0, False)["score_map_ref_cross"]
+        out = self.imgproc.postprocess_scores(score, mean=True, gray16_vrange=self.vrange)
+        means[b].copy_(out["mean"], non_blocking=True)
+        maps[b].copy_(out["gray16"], non_blocking=True)
+        self._step += 1
+        return means[b], maps[b]

@@ -10,3 +10,6 @@ echo "launch list: $(wc -l < gpurun_out/launches.csv) lines"
 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -s 30 -c 1 -o gpurun_out/prof_attn $BENCH > gpurun_out/ncu_attn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 60 -c 4 -o gpurun_out/prof_gemm $BENCH > gpurun_out/ncu_gemm.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+# the pre-/post-processing kernels, full set, one launch each
+ncu --set full --clock-control none --import-source on -k regex:"resize_aa_norm|score_post|u8_norm" -s 12 -c 3 -o gpurun_out/prof_imgproc python tools/prof_imgproc.py > gpurun_out/ncu_imgproc.log 2>&1
+ls -la gpurun_out/prof_imgproc.ncu-rep
