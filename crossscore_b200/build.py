@@ -27,7 +27,15 @@ def _stale(obj, src):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    objdir = os.path.join(HERE, "build")
+    """XS_BUILD_DEFS="-DATT_X=1 ..." + XS_BUILD_TAG=name build a development variant into
+    libcrossscore_sm100a_<name>.so (load it with XS_LIB_PATH) without touching the product library."""
+    tag, defs = os.environ.get("XS_BUILD_TAG", ""), os.environ.get("XS_BUILD_DEFS", "").split()
+    if tag:
+        return _build(os.path.join(HERE, "build_" + tag), LIB.replace(".so", f"_{tag}.so"), defs, True, verbose)
+    return _build(os.path.join(HERE, "build"), LIB, [], force, verbose)
+
+
+def _build(objdir: str, LIB: str, defs, force: bool, verbose: bool) -> str:
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     for s in SOURCES:
@@ -35,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, src):
-            cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+            cmd = [NVCC, *FLAGS, *defs, "-c", src, "-o", obj]
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     rebuilt = bool(procs)
     for s, p in procs:

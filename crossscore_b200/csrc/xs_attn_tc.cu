@@ -33,11 +33,19 @@ constexpr int ATT_THREADS = 256;                        // warpgroup 0: softmax 
 constexpr int ATT_BKV = 64;                             // keys per block
 constexpr int ATT_ST = 5;                               // K and V ring depth
 // Which of the 16 column pairs of a 32-column chunk take the polynomial exponential (FMA pipe) instead of MUFU.EX2.
-// Measured on the DINOv2 shape (I=48): none 0.235 ms, 3/16 0.229 ms, 7/16 0.235 ms, 8/16 0.241 ms, 10/16 0.250 ms --
-// the softmax warps are bound by their own instruction latency chain, not by the MUFU (62 % busy), so only a light
-// offload pays.
+// Measured on the DINOv2 shape (I=48) with the eager hand-over: none 0.235 ms, 3/16 0.228 ms, 4/16 0.229 ms,
+// 5/16 0.227 ms, 6/16 0.231 ms, 8/16 0.242 ms (decoder shape: 0.206 / 0.201 / 0.200 / 0.197 / 0.202 / 0.211 ms) --
+// the softmax warps are paced by the hand-over chain and their own latency, not by the MUFU alone (62 % busy), so
+// only a light offload pays.
 #ifndef ATT_POLY_MASK
-#define ATT_POLY_MASK 0x0888
+#define ATT_POLY_MASK 0x2492
+#endif
+// When the softmax warps hand P_g to the MMA warp: 1 = right after the P store of the block (wait::st + arrive),
+// 0 = deferred behind the next block's first exponentials, 2 = at the top of the next block.  Measured (DINOv2 shape /
+// decoder shape): 0: 0.241 / 0.211 ms, 2: 0.236 / 0.207 ms, 1: 0.228 / 0.201 ms -- the hand-over sits on the
+// MMA -> softmax -> MMA chain that paces the kernel; the ~170 cycles of store latency it exposes are cheaper.
+#ifndef ATT_EAGER_HANDOVER
+#define ATT_EAGER_HANDOVER 1
 #endif
 constexpr int ATT_REGS_SOFTMAX = 200;                   // setmaxnreg budgets (multiples of 8): 4*200 + 4*56 = 8*128
 constexpr int ATT_REGS_CTRL = 56;
@@ -469,7 +477,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         l += bsum;
         pc.lap(2);
         tmem_st16(t_s + 48, pkb);
+#if ATT_EAGER_HANDOVER == 1
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + sb);
+#else
         pending_sb = static_cast<int>(sb);
+#endif
         pc.lap(3);
       };
       for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
@@ -570,10 +585,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
         tmem_ld_wait32(va);
         if (!(DBG && (p.dbg & 4))) tmem_ld32(t_s + 32, vb);  // in flight during chunk A   (dbg 4: no S loads)
+#if ATT_EAGER_HANDOVER == 2
+        flush_pending();  // previous block's P: its store had the load wait above to land
+#endif
         pc.lap(1);
         if constexpr (MASK) mask_tail(va, valid);
         if (j > 0) exp_chunk<DBG>(va, sl2, neg_m, pka, acc0, acc1, p.dbg);
+#if ATT_EAGER_HANDOVER == 0
         flush_pending();  // previous block's P
+#endif
         pc.lap(2);
         tmem_ld_wait32(vb);
         pc.lap(6);  // residual wait for chunk B
@@ -645,7 +665,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         l += bsum;
         pc.lap(2);  // exp2 / pack
         if (!(DBG && (p.dbg & 2))) tmem_st16(t_s + 48, pkb);
+#if ATT_EAGER_HANDOVER == 1
+        tc_wait_st();  // hand P_g over right away: the MMA -> softmax -> MMA chain latency, not the store, is what binds
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + sb);
+#else
         pending_sb = static_cast<int>(sb);
+#endif
         pc.lap(3);  // tcgen05.st of P issued
       };
       for (int j = 0; j + 1 < nkv; ++j) block(j, MaskNo{});
