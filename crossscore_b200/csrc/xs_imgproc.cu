@@ -129,35 +129,54 @@ __global__ void __launch_bounds__(RS_THREADS) resize_aa_norm_kernel(ResizeParams
   }
   __syncthreads();
   // 2. width pass: tmp[r][tx][c] = sum_k wx[tx][k] * lut[raw[r][x0 - xlo + k][c]]   (fp32, taps in ascending order)
-  for (int e = tid; e < nrow * tw; e += RS_THREADS) {
-    const int r = e / tw, tx = e - r * tw;
-    const int xs = x0s[tx] - xlo, n = nxs[tx];
-    const float* w = wx + tx * RS_MAXTAP;
-    const uint8_t* rp = raw + r * raw_pitch + rshift[r] + xs * 3;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int k = 0; k < n; ++k) {
-      const float wk = w[k];
-      a0 = __fadd_rn(a0, __fmul_rn(wk, lut[rp[3 * k + 0]]));
-      a1 = __fadd_rn(a1, __fmul_rn(wk, lut[rp[3 * k + 1]]));
-      a2 = __fadd_rn(a2, __fmul_rn(wk, lut[rp[3 * k + 2]]));
+  //    thread = (row r = tid / 32 + 8 i, column tx = tid % 32): no integer divisions, three channels per thread
+  {
+    const int tx = tid & (RS_TW - 1);
+    if (tx < tw) {
+      const int xs = (x0s[tx] - xlo) * 3, n = nxs[tx];
+      const float* w = wx + tx * RS_MAXTAP;
+      for (int r = tid >> 5; r < nrow; r += RS_THREADS / RS_TW) {
+        const uint8_t* rp = raw + r * raw_pitch + rshift[r] + xs;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int k = 0; k < n; ++k) {
+          const float wk = w[k];
+          a0 = __fadd_rn(a0, __fmul_rn(wk, lut[rp[3 * k + 0]]));
+          a1 = __fadd_rn(a1, __fmul_rn(wk, lut[rp[3 * k + 1]]));
+          a2 = __fadd_rn(a2, __fmul_rn(wk, lut[rp[3 * k + 2]]));
+        }
+        float* t = tmp + (r * RS_TW + tx) * 3;
+        t[0] = a0;
+        t[1] = a1;
+        t[2] = a2;
+      }
     }
-    float* t = tmp + (r * RS_TW + tx) * 3;
-    t[0] = a0;
-    t[1] = a1;
-    t[2] = a2;
   }
   __syncthreads();
-  // 3. height pass + normalise + NCHW store (tx fastest: coalesced rows)
-  for (int e = tid; e < 3 * th * tw; e += RS_THREADS) {
-    const int c = e / (th * tw);
-    const int rem = e - c * (th * tw);
-    const int ty = rem / tw, tx = rem - ty * tw;
-    const int ys = y0s[ty] - ylo, n = nys[ty];
-    const float* w = wy + ty * RS_MAXTAP;
-    float a = 0.f;
-    for (int k = 0; k < n; ++k) a = __fadd_rn(a, __fmul_rn(w[k], tmp[((ys + k) * RS_TW + tx) * 3 + c]));
-    const float v = __fdiv_rn(__fsub_rn(a, p.mean[c]), p.std[c]);  // torchvision Normalize: sub_(mean).div_(std)
-    p.out[((static_cast<size_t>(img) * 3 + c) * p.H1 + (oy0 + ty)) * p.W1 + ox0 + tx] = v;
+  // 3. height pass + normalise + NCHW store: thread = (ty = tid / 32 + 8 i, tx = tid % 32), three channels per
+  //    thread (one weight load per tap), tx fastest so every warp writes 128 contiguous bytes per channel row
+  {
+    const int tx = tid & (RS_TW - 1);
+    if (tx < tw) {
+      const float m0 = p.mean[0], m1 = p.mean[1], m2 = p.mean[2], s0 = p.std[0], s1 = p.std[1], s2 = p.std[2];
+      const size_t plane = static_cast<size_t>(p.H1) * p.W1;
+      for (int ty = tid >> 5; ty < th; ty += RS_THREADS / RS_TW) {
+        const int ys = y0s[ty] - ylo, n = nys[ty];
+        const float* w = wy + ty * RS_MAXTAP;
+        const float* t = tmp + (ys * RS_TW + tx) * 3;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int k = 0; k < n; ++k) {
+          const float wk = w[k];
+          a0 = __fadd_rn(a0, __fmul_rn(wk, t[k * RS_TW * 3 + 0]));
+          a1 = __fadd_rn(a1, __fmul_rn(wk, t[k * RS_TW * 3 + 1]));
+          a2 = __fadd_rn(a2, __fmul_rn(wk, t[k * RS_TW * 3 + 2]));
+        }
+        // torchvision Normalize: sub_(mean).div_(std)
+        float* o = p.out + static_cast<size_t>(img) * 3 * plane + static_cast<size_t>(oy0 + ty) * p.W1 + ox0 + tx;
+        o[0] = __fdiv_rn(__fsub_rn(a0, m0), s0);
+        o[plane] = __fdiv_rn(__fsub_rn(a1, m1), s1);
+        o[2 * plane] = __fdiv_rn(__fsub_rn(a2, m2), s2);
+      }
+    }
   }
 }
 
