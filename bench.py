@@ -68,6 +68,18 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
 
 
+def ncu_traffic(kernel_tag):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture of this same command (profiles/traffic.json, written from profiles/*_ncu_*.txt), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(kernel_tag)
+        except Exception:
+            return None
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -247,13 +259,13 @@ def run_ours(args):
     if tent[1] > 0:
         ach = tent[1] / tent[0] / (tent[3] / tent[0] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor_sustained"], "traffic": None,
+                "frac": ach / pk["tensor_sustained"], "traffic": ncu_traffic(top),
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": tent[1] / tent[0], "avg_launch_ms": tent[3] / tent[0]}
     else:
         ach = tent[2] / tent[0] / (tent[3] / tent[0] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"]}
+                "frac": ach / pk["hbm"], "traffic": ncu_traffic(top), "peak_source": pk["source"]}
     attn_fl = sum(a[1] for t, a in agg.items() if t.startswith("attn_") and a[1] > 0)
     attn_ms = sum(a[3] for t, a in agg.items() if t.startswith("attn_") and a[1] > 0)
     attn_tf = attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0

@@ -333,6 +333,9 @@ def main(argv=None):
     path = runner.write_summary()
     torch.cuda.synchronize()
     print(f"[rank {rank}] wrote {len(runner.rows)} scores to {path}")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
