@@ -229,6 +229,24 @@ def run_ours(args):
                 "stages": "uint8 HWC host images -> H2D -> xs_preprocess_u8_resize_normalize -> CrossScoreNet.forward -> "
                           "xs_score_postprocess (frame mean + uint16 map) -> D2H"}
 
+    # ---- single-query latency (BASELINE cfg 1: 1 query + 5 refs): eager launches vs one CUDA graph replay ----------
+    from crossscore_b200.runner import GraphedScorer
+    q1, r1 = q_dev[:1].contiguous(), r_dev[:1].contiguous()
+    graphed = GraphedScorer(net, dev)
+    graphed(q1, r1)
+    lat = {}
+    for name, fn in (("eager", lambda: net(q1, r1, False, 0, False)), ("cuda_graph", lambda: graphed(q1, r1))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        lat[name + "_ms"] = e0.elapsed_time(e1) / 20
+    latency = {"workload": "cfg1: 1 query x 5 refs, 518x518, device-resident inputs", **lat}
+
     # ---- per-kernel roofline (instrumented pass, CUDA events on the launching stream) --------------------
     eng = net._engine(dev)
     eng.prof = []
@@ -297,6 +315,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "maps/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": scorer.h2d_bytes(qh, rh), "d2h_bytes_per_step": int(host_out.numel() * 4)},
         "pipeline": pipeline,
+        "latency_cfg1": latency,
         "gpu_launches": launches,
         "clocks": clocks,
         "model_tflops": value * fpm / 1e12,

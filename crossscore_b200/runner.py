@@ -120,3 +120,44 @@ class HostPipeline:
         maps[b].copy_(out["gray16"], non_blocking=True)
         self._step += 1
         return means[b], maps[b]
+
+
+class GraphedScorer:
+    """The forward of one fixed input shape captured into a CUDA graph and replayed.
+
+    A single query with its references (BASELINE cfg 1) is launch-bound: ~115 kernel launches of a few microseconds
+    each.  Every C-ABI entry only enqueues on the caller's stream and the engine's workspaces are persistent, so the
+    whole forward captures as is; replaying it costs one launch.  Inputs are copied into the graph's static buffers
+    (device-to-device), the returned score map is the graph's static output (valid until the next call)."""
+
+    def __init__(self, net, device="cuda:0", warmup: int = 2):
+        self.net, self.device, self.warmup = net, torch.device(device), warmup
+        self._key = None
+        self._graph = None
+
+    def _capture(self, q, r):
+        self._q = torch.empty_like(q, device=self.device)
+        self._r = torch.empty_like(r, device=self.device)
+        self._q.copy_(q)
+        self._r.copy_(r)
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up off the capture: builds workspaces, tables and packed weights
+            for _ in range(self.warmup):
+                self.net(self._q, self._r, False, 0, False)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._out = self.net(self._q, self._r, False, 0, False)["score_map_ref_cross"]
+        self._key = (tuple(q.shape), tuple(r.shape))
+
+    def __call__(self, q: torch.Tensor, r: torch.Tensor) -> torch.Tensor:
+        if self._key != (tuple(q.shape), tuple(r.shape)):
+            self._capture(q, r)
+        else:
+            self._q.copy_(q, non_blocking=True)
+            self._r.copy_(r, non_blocking=True)
+        self._graph.replay()
+        return self._out

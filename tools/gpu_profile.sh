@@ -7,7 +7,7 @@ BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 240 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
 echo "launch list: $(wc -l < gpurun_out/launches.csv) lines"
 # the top kernels, full set, one launch each (after warm-up launches)
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"attn_tc_kernel<4, 64" -s 30 -c 1 -o gpurun_out/prof_attn $BENCH > gpurun_out/ncu_attn.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"attn_tc_kernel<.int.4" -s 30 -c 1 -o gpurun_out/prof_attn $BENCH > gpurun_out/ncu_attn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 60 -c 4 -o gpurun_out/prof_gemm $BENCH > gpurun_out/ncu_gemm.log 2>&1
 ls -la gpurun_out/*.ncu-rep
 # the pre-/post-processing kernels, full set, one launch each
