@@ -159,12 +159,37 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, th, hx);
 }
 
+// the same GELU on a pair of values with packed fp32x2 FMAs (bit-identical to gelu_erf_fast: same operations, same
+// roundings; 13 issue slots per pair instead of 20 -- the fc1 epilogue is issue-bound next to its tile's MMAs)
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 zero = make_float2(0.f, 0.f);
+  float2 x2 = ffma2(x, x, zero);
+  x2.x = fminf(x2.x, 64.0f);
+  x2.y = fminf(x2.y, 64.0f);
+  float2 t = ffma2(make_float2(-3.51516783e-04f, -3.51516783e-04f), x2, make_float2(3.70056460e-02f, 3.70056460e-02f));
+  t = ffma2(t, x2, make_float2(7.97507884e-01f, 7.97507884e-01f));
+  const float2 u = ffma2(x, t, zero);
+  const float2 th = make_float2(fast_tanh(u.x), fast_tanh(u.y));
+  const float2 hx = ffma2(x, make_float2(0.5f, 0.5f), zero);
+  return ffma2(hx, th, hx);
+}
+
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
   if constexpr (ACT == ACT_GELU) return gelu_erf_fast(v);
   if constexpr (ACT == ACT_RELU) return fmaxf(v, 0.0f);
   if constexpr (ACT == ACT_LEAKY) return v >= 0.0f ? v : 0.01f * v;
   return v;
+}
+
+// act(v0 + b0), act(v1 + b1) for a pair of accumulator values (packed path for GELU)
+template <int ACT>
+__device__ __forceinline__ float2 bias_act2(float v0, float v1, float b0, float b1) {
+  if constexpr (ACT == ACT_GELU) {
+    return gelu_erf_fast2(fadd2(make_float2(v0, v1), make_float2(b0, b1)));
+  } else {
+    return make_float2(apply_act<ACT>(v0 + b0), apply_act<ACT>(v1 + b1));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -370,14 +370,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 ba = __ldg(b4 + j * 2), bb = __ldg(b4 + j * 2 + 1);
               const int o = j * 8;
               uint4 pk;
-              pk.x = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 0]) + ba.x),
-                                 apply_act<ACT>(__uint_as_float(vv[o + 1]) + ba.y));
-              pk.y = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 2]) + ba.z),
-                                 apply_act<ACT>(__uint_as_float(vv[o + 3]) + ba.w));
-              pk.z = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 4]) + bb.x),
-                                 apply_act<ACT>(__uint_as_float(vv[o + 5]) + bb.y));
-              pk.w = pack_out16<OUT>(apply_act<ACT>(__uint_as_float(vv[o + 6]) + bb.z),
-                                 apply_act<ACT>(__uint_as_float(vv[o + 7]) + bb.w));
+              const float2 r0 = bias_act2<ACT>(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1]), ba.x, ba.y);
+              const float2 r1 = bias_act2<ACT>(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3]), ba.z, ba.w);
+              const float2 r2 = bias_act2<ACT>(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5]), bb.x, bb.y);
+              const float2 r3 = bias_act2<ACT>(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7]), bb.z, bb.w);
+              pk.x = pack_out16<OUT>(r0.x, r0.y);
+              pk.y = pack_out16<OUT>(r1.x, r1.y);
+              pk.z = pack_out16<OUT>(r2.x, r2.y);
+              pk.w = pack_out16<OUT>(r3.x, r3.y);
               *reinterpret_cast<uint4*>(rp + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
             }
           } else {
