@@ -185,11 +185,9 @@ __device__ __forceinline__ float apply_act(float v) {
 // act(v0 + b0), act(v1 + b1) for a pair of accumulator values (packed path for GELU)
 template <int ACT>
 __device__ __forceinline__ float2 bias_act2(float v0, float v1, float b0, float b1) {
-  if constexpr (ACT == ACT_GELU) {
-    return gelu_erf_fast2(fadd2(make_float2(v0, v1), make_float2(b0, b1)));
-  } else {
-    return make_float2(apply_act<ACT>(v0 + b0), apply_act<ACT>(v1 + b1));
-  }
+  const float2 x = fadd2(make_float2(v0, v1), make_float2(b0, b1));  // one FADD2 for the two bias adds
+  if constexpr (ACT == ACT_GELU) return gelu_erf_fast2(x);
+  else return make_float2(apply_act<ACT>(x.x), apply_act<ACT>(x.y));
 }
 
 // ---------------------------------------------------------------------------------------------
