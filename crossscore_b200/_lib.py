@@ -35,6 +35,7 @@ SIGNATURES = {
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_lse_merge": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _i, _p]),
     "xs_head_score_jigsaw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "xs_lse_merge_peers": (_i, [_p, _ll, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "xs_preprocess_u8_resize_normalize": (_i, [_p, _i, _i, _i, _p, _i, _i, C.POINTER(C.c_float), _p]),
     "xs_score_postprocess": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _f, _f, _p, _sz, _p]),
     "xs_attn_probs_one_head": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p]),

@@ -103,6 +103,8 @@ int table_bilinear_ac(const float*, float*, int, int, int, int, int, cudaStream_
 int table_bicubic(const float*, float*, int, int, int, int, int, cudaStream_t);
 int rows_lse_merge(const float*, const float*, void*, float*, int, int, int, int, int, long long, long long, int,
                    cudaStream_t);
+int rows_lse_merge_peers(const void* const*, long long, long long, void*, float*, int, int, int, int, int, int,
+                         cudaStream_t);
 int rows_attn_probs(const void*, const void*, const float*, float*, int, int, int, int, int, int, int, long long,
                     long long, long long, long long, float, int, cudaStream_t);
 
@@ -245,6 +247,13 @@ int xs_head_score_jigsaw(const void* A, int lda, const void* W, int ldw, const f
                            pw, K, use_tanh, power, st);
   set_last_error("head_score_jigsaw: unknown dtype %d", dtype);
   return -1;
+}
+
+int xs_lse_merge_peers(const void* const* part_ptrs, long long base_elems, long long lse_offset_elems, void* out,
+                       float* lse_out, int n_parts, int B, int Lq, int heads, int head_dim, int out_dtype,
+                       xs_stream_t stream) {
+  return rows_lse_merge_peers(part_ptrs, base_elems, lse_offset_elems, out, lse_out, n_parts, B, Lq, heads, head_dim,
+                              out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int xs_preprocess_u8_resize_normalize(const uint8_t* img, int n, int H0, int W0, float* out, int H1, int W1,

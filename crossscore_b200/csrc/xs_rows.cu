@@ -341,6 +341,39 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
   }
 }
 
+// The same merge fused with its collective: parts[s] is the packed (O_s | LSE_s) buffer of rank s, read IN PLACE
+// through NVLink peer pointers (symmetric memory), so the multi-GPU split-KV path needs no all-gather and no gathered
+// buffer: one cross-rank barrier, then every rank pulls the R partials while it merges.
+template <typename AT>
+__global__ void __launch_bounds__(256) lse_merge_peers_kernel(const float* const* __restrict__ parts, long long base,
+                                                              long long lse_off, AT* __restrict__ out,
+                                                              float* __restrict__ lse_out, int R, int B, int Lq,
+                                                              int heads, int d) {
+  const long long total = static_cast<long long>(B) * Lq * heads * d;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(idx % d);
+    const int hh = static_cast<int>((idx / d) % heads);
+    const long long rowg = idx / (static_cast<long long>(d) * heads);
+    const int b = static_cast<int>(rowg / Lq);
+    const int r = static_cast<int>(rowg - static_cast<long long>(b) * Lq);
+    const long long li = (static_cast<long long>(b) * heads + hh) * Lq + r;
+    float mx = -INFINITY;
+    for (int s = 0; s < R; ++s) mx = fmaxf(mx, parts[s][base + lse_off + li]);
+    float den = 0.f, acc = 0.f;
+    for (int s = 0; s < R; ++s) {
+      const float* ps = parts[s] + base;
+      const float w = expf(ps[lse_off + li] - mx);
+      den += w;
+      acc += w * ps[idx];
+    }
+    const float v = acc / den;
+    if constexpr (sizeof(AT) == 2) out[idx] = __float2bfloat16_rn(v);
+    else out[idx] = v;
+    if (lse_out != nullptr && e == 0) lse_out[li] = mx + logf(den);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // attention probabilities of ONE head (debug/visualisation path, need_attn_weights=True;
 // model/customised_transformer/transformer.py:175-178, model/cross_reference.py:91-93):
@@ -473,6 +506,18 @@ int rows_lse_merge(const float* o_parts, const float* lse_parts, void* out, floa
   XS_DISPATCH_AT(dtype, (lse_merge_kernel<AT><<<grid_for(total), 256, 0, stream>>>(
                             o_parts, lse_parts, static_cast<AT*>(out), lse_out, R, B, Lq, heads, d, o_part_stride,
                             lse_part_stride)));
+  XS_LAUNCH_CHECK();
+  return 0;
+}
+
+int rows_lse_merge_peers(const void* const* parts, long long base, long long lse_off, void* out, float* lse_out, int R,
+                         int B, int Lq, int heads, int d, int dtype, cudaStream_t stream) {
+  XS_CHECK_ARG(parts != nullptr && R > 0 && B > 0 && Lq > 0 && heads > 0 && d > 0, "lse_merge_peers: bad dims");
+  const long long total = static_cast<long long>(B) * Lq * heads * d;
+  XS_CHECK_ARG(base >= 0 && lse_off >= total, "lse_merge_peers: LSE offset %lld overlaps O (%lld elements)", lse_off, total);
+  XS_DISPATCH_AT(dtype, (lse_merge_peers_kernel<AT><<<grid_for(total), 256, 0, stream>>>(
+                            reinterpret_cast<const float* const*>(parts), base, lse_off, static_cast<AT*>(out), lse_out,
+                            R, B, Lq, heads, d)));
   XS_LAUNCH_CHECK();
   return 0;
 }

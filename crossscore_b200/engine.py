@@ -479,6 +479,14 @@ class Engine:
             call("xs_lse_merge", _ptr(gathered), gathered.data_ptr() + B * P * C * 4, _ptr(att), _ptr(lse_out),
                  n_parts, B, P, DEC_HEADS, DEC_D, part, part, DT_F32, st)
 
+    def merge_partials_peers(self, ptrs_dev: int, base: int, n_parts, B, P, att, lse_out, st):
+        """Same merge, pulling each rank's packed (O_r | LSE_r) buffer through its NVLink peer pointer
+        (ptrs_dev: device array of n_parts pointers; base: element offset of this layer's buffer)."""
+        part = B * P * C + B * DEC_HEADS * P
+        with self._op("lse_merge_peers", 0.0, n_parts * part * 4.0 + att.numel() * 4.0):
+            call("xs_lse_merge_peers", ptrs_dev, base, B * P * C, _ptr(att), _ptr(lse_out), n_parts, B, P, DEC_HEADS,
+                 DEC_D, DT_F32, st)
+
     # ---- the reference-shaped forward ------------------------------------------------------------
     def forward(self, query_img, ref_imgs, need_attn_weights=False, head_id=0):
         if need_attn_weights and not 0 <= head_id < DEC_HEADS:

@@ -25,6 +25,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -137,12 +139,33 @@ class SplitKVScorer:
     ``merge_partials(gathered, n_parts, B, P, att, lse_out, st)`` merges ``n_parts`` packed parts.
     """
 
-    def __init__(self, engine, device, group=None):
+    def __init__(self, engine, device, group=None, exchange: Optional[str] = None):
+        """exchange: how the per-rank partials meet.  "p2p" (default with more than one rank): each rank writes its
+        packed (O_r | LSE_r) into a symmetric-memory buffer and the merge kernel PULLS all partials through NVLink peer
+        pointers after one cross-rank barrier -- compute and collective in one kernel (xs_lse_merge_peers).
+        "nccl": one all_gather_into_tensor per decoder layer, then xs_lse_merge (also the automatic choice when
+        symmetric memory cannot be set up, e.g. no peer access)."""
         self.engine = engine
         self.device = torch.device(device)
         self.group = group
         self.world, self.rank = _dist_info(group)
         self.allgather_bytes = 0
+        self.exchange = exchange or os.environ.get("XS_SPLITKV_EXCHANGE", "p2p")
+        if self.exchange not in ("p2p", "nccl"):
+            raise ValueError(f"exchange must be 'p2p' or 'nccl', got {self.exchange!r}")
+        if self.world == 1 or self.device.type != "cuda":
+            self.exchange = "nccl"  # nothing to exchange / host-side tests of the schedule (gloo)
+        self._symm = None       # (part elements, tensor, handle)
+        self.peer_bytes_pulled = 0
+
+    def _symm_buffers(self, part: int):
+        """Two symmetric packed buffers (one per decoder layer) of `part` floats each, rendezvoused across the ranks."""
+        if self._symm is None or self._symm[0] != part:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(DEC_LAYERS * part, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self._symm = (part, t, hdl)
+        return self._symm[1], self._symm[2]
 
     def forward(self, query_img: torch.Tensor, ref_imgs: torch.Tensor) -> torch.Tensor:
         """query_img (B,3,H,W), ref_imgs (B,N,3,H,W) identical on every rank -> (B,14ph,14pw) score maps,
@@ -159,23 +182,39 @@ class SplitKVScorer:
         xq32, mem = eng.features(query_img.contiguous(), refs_loc, st)
         kv_loc = eng.project_kv(mem, st) if n_loc else None
         part = B * P * C + B * DEC_HEADS * P
-        packed = torch.empty(part, device=self.device, dtype=torch.float32)
-        gathered = torch.empty(self.world * part, device=self.device, dtype=torch.float32)
         self.allgather_bytes = 0
+        self.peer_bytes_pulled = 0
+        symm_t = hdl = None
+        if self.exchange == "p2p":
+            try:
+                symm_t, hdl = self._symm_buffers(part)
+            except Exception as e:  # no peer access / symmetric memory backend: use the NCCL collective
+                import warnings
+                warnings.warn(f"split-KV: symmetric memory unavailable ({e}); exchanging partials with NCCL all-gather")
+                self.exchange = "nccl"
+        if self.exchange == "nccl":
+            packed_nccl = torch.empty(part, device=self.device, dtype=torch.float32)
+            gathered = torch.empty(self.world * part, device=self.device, dtype=torch.float32) if self.world > 1 else None
 
         def cross_attn(layer, qc, att, lse_out, st_):
+            packed = symm_t[layer * part:(layer + 1) * part] if hdl is not None else packed_nccl
             if n_loc:
                 eng.cross_attn_partial(layer, qc, kv_loc, B, P, M_loc, packed, st_)
             else:  # this rank owns no reference view: neutral element of the merge
                 packed[:B * P * C].zero_()
                 packed[B * P * C:].fill_(float("-inf"))
-            if self.world > 1:
+            if hdl is not None:
+                # every rank's partial of this layer is in place after the barrier; the buffer of this layer is not
+                # rewritten before the next query's barrier of the OTHER layer has been passed by all ranks
+                hdl.barrier(channel=layer)
+                eng.merge_partials_peers(hdl.buffer_ptrs_dev, layer * part, self.world, B, P, att, lse_out, st_)
+                self.peer_bytes_pulled += (self.world - 1) * part * 4
+            elif self.world > 1:
                 dist.all_gather_into_tensor(gathered, packed, group=self.group)
                 self.allgather_bytes += gathered.numel() * 4
-                src = gathered
+                eng.merge_partials(gathered, self.world, B, P, att, lse_out, st_)
             else:
-                src = packed
-            eng.merge_partials(src, self.world, B, P, att, lse_out, st_)
+                eng.merge_partials(packed, 1, B, P, att, lse_out, st_)
 
         score, _ = eng.decode(xq32, None, B, P, N * P, ph, pw, st, cross_attn_fn=cross_attn)
         return score

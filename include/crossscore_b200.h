@@ -147,6 +147,16 @@ int xs_attn_probs_one_head(const void* q, const void* k, const float* lse, float
                            long long q_batch_stride, long long kv_row_stride, long long kv_batch_stride,
                            float scale, int dtype, xs_stream_t stream);
 
+/* C2'  the split-KV merge fused with its collective: part_ptrs is a DEVICE array of n_parts pointers, entry s = the
+ *     packed fp32 buffer of rank s (peer memory mapped over NVLink, e.g. torch symmetric memory buffer_ptrs_dev):
+ *     normalised partial O (B*Lq*heads*head_dim) at base_elems, its LSE (B*heads*Lq) at base_elems + lse_offset_elems.
+ *     Every rank pulls the partials in place while merging: no all-gather, no gathered buffer.  The caller orders the
+ *     ranks (all partials written before, all merges done before the buffers are rewritten) with a cross-rank barrier
+ *     on the stream. */
+int xs_lse_merge_peers(const void* const* part_ptrs, long long base_elems, long long lse_offset_elems, void* out,
+                       float* lse_out, int n_parts, int B, int Lq, int heads, int head_dim, int out_dtype,
+                       xs_stream_t stream);
+
 /* ---- the steps either side of the path ---------------------------------- */
 
 /* F2  uint8 HWC image(s) -> /255 -> antialiased bilinear resize -> ImageNet normalise -> fp32 NCHW: the dataloader's

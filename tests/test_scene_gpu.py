@@ -97,7 +97,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, mode, precision, n_ref, n_query, ret):
+def _worker(rank, world, port, mode, precision, n_ref, n_query, ret, exchange="p2p"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -110,18 +110,22 @@ def _worker(rank, world, port, mode, precision, n_ref, n_query, ret):
             sc = SceneScorer(eng, dev)
             out = sc.score_scene(q.to(dev), refs.to(dev), batch=2)
         else:
-            sk = SplitKVScorer(eng, dev)
-            out = sk.forward(q.to(dev), refs[None].expand(n_query, -1, -1, -1, -1).contiguous().to(dev))
+            sk = SplitKVScorer(eng, dev, exchange=exchange)
+            rr = refs[None].expand(n_query, -1, -1, -1, -1).contiguous().to(dev)
+            out = sk.forward(q.to(dev), rr).clone()
+            out2 = sk.forward(q.to(dev), rr)  # second query: the symmetric buffers are reused
+            assert torch.equal(out, out2)
+            ret[f"exchange{rank}"] = sk.exchange
         torch.cuda.synchronize()
         ret[rank] = out.cpu()
     finally:
         dist.destroy_process_group()
 
 
-def _run(mode, precision, n_ref, n_query):
+def _run(mode, precision, n_ref, n_query, exchange="p2p"):
     import torch.multiprocessing as mp
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), mode, precision, n_ref, n_query, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), mode, precision, n_ref, n_query, ret, exchange), nprocs=2, join=True)
     return dict(ret)
 
 
@@ -141,11 +145,15 @@ def test_scene_cache_two_gpus_nccl(precision):
 
 
 @needs2
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("precision,n_ref", [("fp32", 3), ("bf16", 3), ("bf16", 1)])
-def test_split_kv_two_gpus_nccl(precision, n_ref):
+def test_split_kv_two_gpus(precision, n_ref, exchange):
+    """exchange = p2p: partials pulled through NVLink peer pointers inside the merge kernel (symmetric memory);
+    nccl: all-gather + merge.  Both must give the single-GPU answer."""
     sd, q, refs = _problem(n_ref, 2)
     want = _want(sd, q, refs)
-    ret = _run("split", precision, n_ref, 2)
+    ret = _run("split", precision, n_ref, 2, exchange)
+    assert ret["exchange0"] == ret["exchange1"] == exchange  # p2p must really run as p2p on an NVLink box
     assert torch.equal(ret[0], ret[1])  # the replicated decoder stream ends identical on both ranks
     err = (ret[0].double() - want).abs()
     assert err.max().item() <= TOL[precision][0] and err.mean().item() <= TOL[precision][1]
