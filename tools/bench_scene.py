@@ -39,38 +39,42 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 out = {"n_gpus": world}
 with torch.inference_mode():
     # ---------------- cfg 3 ----------------
-    _, refs = make_inputs(1, 5, 518, 518, seed=7)
-    refs = refs[0].to(dev)
-    lo, hi = shard_range(Q, world, rank)
-    q_mine, _ = make_inputs(32, 1, 518, 518, seed=100 + rank)   # one resident batch reused for the rank's share
-    q_mine = q_mine.to(dev)
-    sc = SceneScorer(eng, dev)
-    sc.build_reference_cache(refs); sc.score(q_mine)            # warm-up
-    barrier(); e0.record()
-    sc.build_reference_cache(refs)
-    e1.record(); barrier()
-    ms_cache = tmax(e0.elapsed_time(e1))
-    n_batches = (hi - lo + 31) // 32
-    barrier(); e0.record()
-    for _ in range(n_batches):
-        s = sc.score(q_mine)
-    e1.record(); barrier()
-    ms_score = tmax(e0.elapsed_time(e1))
-    out["cfg3"] = {"queries": Q, "refs": 5, "cache_build_ms": ms_cache, "cache_bytes_received_per_rank": sc.cache_bytes_received,
-                   "score_ms": ms_score, "maps_per_s_excl_cache": Q / (ms_score * 1e-3),
-                   "maps_per_s_incl_cache": Q / ((ms_score + ms_cache) * 1e-3),
-                   "note": "per-map work 135.0 GF (queries only; SURVEY 8d), inputs device-resident"}
+    if os.environ.get("SKIP_CFG3") != "1":
+      _, refs = make_inputs(1, 5, 518, 518, seed=7)
+      refs = refs[0].to(dev)
+      lo, hi = shard_range(Q, world, rank)
+      q_mine, _ = make_inputs(32, 1, 518, 518, seed=100 + rank)   # one resident batch reused for the rank's share
+      q_mine = q_mine.to(dev)
+      sc = SceneScorer(eng, dev)
+      sc.build_reference_cache(refs); sc.score(q_mine)            # warm-up
+      barrier(); e0.record()
+      sc.build_reference_cache(refs)
+      e1.record(); barrier()
+      ms_cache = tmax(e0.elapsed_time(e1))
+      n_batches = (hi - lo + 31) // 32
+      barrier(); e0.record()
+      for _ in range(n_batches):
+          s = sc.score(q_mine)
+      e1.record(); barrier()
+      ms_score = tmax(e0.elapsed_time(e1))
+      out["cfg3"] = {"queries": Q, "refs": 5, "cache_build_ms": ms_cache, "cache_bytes_received_per_rank": sc.cache_bytes_received,
+                     "score_ms": ms_score, "maps_per_s_excl_cache": Q / (ms_score * 1e-3),
+                     "maps_per_s_incl_cache": Q / ((ms_score + ms_cache) * 1e-3),
+                     "note": "per-map work 135.0 GF (queries only; SURVEY 8d), inputs device-resident"}
     # ---------------- cfg 4 ----------------
     q1, r64 = make_inputs(1, 64, 518, 518, seed=9)
     q1, r64 = q1.to(dev), r64.to(dev)
-    sk = SplitKVScorer(eng, dev)
-    got = sk.forward(q1, r64).clone()
-    barrier(); e0.record()
-    for _ in range(5):
+    out["cfg4"] = {"refs": 64}
+    for mode in (("p2p", "nccl") if world > 1 else ("nccl",)):
+        sk = SplitKVScorer(eng, dev, exchange=mode)
+        got = sk.forward(q1, r64).clone()
         sk.forward(q1, r64)
-    e1.record(); barrier()
-    ms_split = tmax(e0.elapsed_time(e1)) / 5
-    out["cfg4"] = {"refs": 64, "ms_per_query_split_kv": ms_split, "allgather_bytes_per_query": sk.allgather_bytes}
+        barrier(); e0.record()
+        for _ in range(10):
+            sk.forward(q1, r64)
+        e1.record(); barrier()
+        out["cfg4"][f"ms_per_query_split_kv_{sk.exchange}"] = tmax(e0.elapsed_time(e1)) / 10
+        out["cfg4"][f"exchange_bytes_per_query_{sk.exchange}"] = sk.allgather_bytes or sk.peer_bytes_pulled
     if rank == 0:
         full = net(q1, r64, False, 0, False)["score_map_ref_cross"]
         torch.cuda.synchronize(); e0.record()
