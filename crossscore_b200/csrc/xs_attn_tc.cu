@@ -4,18 +4,20 @@
 // nn.MultiheadAttention's scaled-dot-product core in the decoder's self- and cross-attention blocks
 // (model/customised_transformer/transformer.py:182-205 -> $SP/torch/nn/functional.py:6630-6692, 8 heads x 48).
 //
-// One CTA = one (batch, head, 128-query tile, kv split); two CTAs are co-resident per SM.  192 threads:
-//   warp 0      TMA producer: Q tile once, then K_j / V_j tiles [64 keys x 64] into a 4-stage ring
-//   warp 1      TMEM allocator + MMA issuer:  S_b = Q K_j^T  (SS, K-major operands, 128B swizzle, N = 64)
+// Persistent CTAs (two per SM) walk a static list of tiles = (batch, kv split, head, 128-query tile).  256 threads:
+//   warps 0..3  softmax: thread == query row (tcgen05.ld 32x32b, TMEM lane quarter = warp id).  A 64-key block is two
+//               32-column chunks, software-pipelined (chunk B's load flies during chunk A's exponentials, the next
+//               block's chunk A during chunk B's).  P = exp2(S*scale - m) against a STALE reference max m: the block's
+//               row sum is the overflow detector, the true max is taken (and l, O rescaled) only when it trips, so the
+//               fast path has no max reduction.  P goes back to TMEM as bf16 over the upper half of its S buffer and is
+//               handed to the MMA warp right after its store; final O / l and log-sum-exp in the epilogue.
+//   warp 4      TMA producer: Q tile per tile, then K_j / V_j tiles [64 keys x 64] into a 5-stage ring
+//   warp 5      TMEM allocator + MMA issuer:  S_b = Q K_j^T  (SS, K-major operands, 128B swizzle, N = 64)
 //                                             O  += P_j V_j  (TS: P read from TMEM, V MN-major from smem)
-//   warps 2..5  softmax: thread == query row (tcgen05.ld 32x32b), one pass over the 64 columns held in
-//               registers: max, lazy O rescale (only when the running max grows by > 2^8), P = exp2(S*scale - m)
-//               written back to TMEM as bf16 over the S columns, final O / l and log-sum-exp.
-// S is TRIPLE-BUFFERED in TMEM (S_0..S_2): QK_{j+3} is issued right behind PV_j, so S_{j+1} is already
-// complete when the softmax finishes block j and the MMA->softmax->MMA handshake latency (measured ~2k
-// cycles per round trip, several times the MMA cycles of a block) is off the critical path; the softmax
-// warps stream continuously and the kernel runs at the exp (MUFU, 16/clk/SM) bound rather than on latency.
-// Barrier traffic is per warp: lane 0 polls / arrives, __syncwarp broadcasts.
+//   warps 6..7  idle (they only lend their registers: setmaxnreg moves 4*200 + 4*56 = 8*128)
+// S is TRIPLE-BUFFERED in TMEM (S_0..S_2): QK_{j+3} is issued right behind PV_j, so the softmax warps normally find
+// S_{j+1} complete when they finish block j.  Barrier traffic is per warp: lane 0 polls / arrives, __syncwarp
+// broadcasts.
 // TMEM (256 columns, two CTAs per SM): S_b [64b, 64b+64), b = 0..2 (P_b aliases the last 32 columns of S_b),
 // O [192, 192+DV).
 // Head dim 48 (decoder) uses 64-wide padded head slots in global memory: QK^T issues 3 K-steps (48) and
