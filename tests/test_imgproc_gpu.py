@@ -81,3 +81,53 @@ def test_postprocess_edge_values():
     m = torch.tensor([[[-0.5, 0.0, 1.0, 1.5], [float("nan"), 0.5, 0.25, 0.75]]], device=DEV)
     out = imgproc.postprocess_scores(m, mean=False, rgb_vrange=(0, 1))
     assert np.array_equal(out["rgb"].cpu().numpy(), IO.gray2rgb_turbo(m.cpu().numpy(), (0, 1)))
+
+
+def test_abi_argument_errors():
+    """Error convention of the new entries: negative status + message, never a crash (include/crossscore_b200.h)."""
+    import ctypes
+    from crossscore_b200 import _lib
+    from crossscore_b200._lib import call
+    st = torch.cuda.current_stream().cuda_stream
+    u8 = torch.zeros(1, 600, 600, 3, dtype=torch.uint8, device=DEV)
+    out = torch.empty(1, 3, 40, 40, device=DEV)
+    ms = (ctypes.c_float * 6)(0.5, 0.5, 0.5, 0.2, 0.2, 0.2)
+    with pytest.raises(_lib.XsError, match="too large"):       # 15x down-scaling: beyond the tap table
+        call("xs_preprocess_u8_resize_normalize", u8.data_ptr(), 1, 600, 600, out.data_ptr(), 40, 40, ms, st)
+    with pytest.raises(_lib.XsError):
+        call("xs_preprocess_u8_resize_normalize", u8.data_ptr(), 0, 600, 600, out.data_ptr(), 40, 40, ms, st)
+    s = torch.zeros(1, 8, 8, device=DEV)
+    with pytest.raises(_lib.XsError, match="vrange_mode"):
+        call("xs_score_postprocess", s.data_ptr(), 1, 8, 8, None, None, 2, None, 0.0, 1.0, None, 0, st)
+    with pytest.raises(_lib.XsError, match="workspace"):       # frame means need the partial-sum workspace
+        m = torch.empty(1, device=DEV)
+        call("xs_score_postprocess", s.data_ptr(), 1, 8, 8, m.data_ptr(), None, 0, None, 0.0, 1.0, None, 0, st)
+    with pytest.raises(_lib.XsError, match="colour range"):
+        rgb = torch.empty(1, 8, 8, 3, dtype=torch.uint8, device=DEV)
+        call("xs_score_postprocess", s.data_ptr(), 1, 8, 8, None, None, 0, rgb.data_ptr(), 1.0, 1.0, None, 0, st)
+    ptrs = torch.zeros(2, dtype=torch.int64, device=DEV)
+    o = torch.empty(4, 384, device=DEV)
+    with pytest.raises(_lib.XsError, match="overlaps"):
+        call("xs_lse_merge_peers", ptrs.data_ptr(), 0, 10, o.data_ptr(), None, 2, 1, 4, 8, 48, 1, st)
+
+
+def test_lse_merge_peers_single_process():
+    """The peer-pointer merge on local buffers (pointer array of two ordinary allocations) == xs_lse_merge."""
+    from crossscore_b200._lib import call
+    torch.manual_seed(1)
+    R, B, P, Hh, d = 2, 2, 37, 8, 48
+    Cc = Hh * d
+    part = B * P * Cc + B * Hh * P
+    bufs = [torch.randn(2 * part, device=DEV) for _ in range(R)]          # two "layers" per buffer; use layer 1
+    for b in bufs:
+        b[part + B * P * Cc:] *= 3
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    got, lse_got = torch.empty(B * P, Cc, device=DEV), torch.empty(B, Hh, P, device=DEV)
+    call("xs_lse_merge_peers", ptrs.data_ptr(), part, B * P * Cc, got.data_ptr(), lse_got.data_ptr(), R, B, P, Hh, d, 1, st)
+    packed = torch.stack([b[part:] for b in bufs]).contiguous()
+    want, lse_want = torch.empty(B * P, Cc, device=DEV), torch.empty(B, Hh, P, device=DEV)
+    call("xs_lse_merge", packed.data_ptr(), packed.data_ptr() + B * P * Cc * 4, want.data_ptr(), lse_want.data_ptr(),
+         R, B, P, Hh, d, part, part, 1, st)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(lse_got, lse_want)

@@ -427,3 +427,11 @@ def test_attn_probs_one_head(dt):
     call("xs_attn_probs_one_head", P(q), P(k), P(lse), P(probs), B, H, head, Lq, Lk, d, slot, H * slot, Lq * H * slot,
          H * slot, Lk * H * slot, scale, dt, st())
     assert (probs.double() - torch.softmax(s, -1)).abs().max() < 1e-5
+
+
+def test_gemm_bias_residual_rejects_bad_shapes():
+    A = rnd(128, 384, dtype=torch.bfloat16)
+    W = rnd(200, 384, dtype=torch.bfloat16)
+    b, h = rnd(200), rnd(128, 200)
+    with pytest.raises(_lib.XsError):      # N must be a multiple of 192
+        call("xs_gemm_bias_residual", P(A), 384, P(W), 384, P(b), P(h), 200, 128, 200, 384, DT_BF16, st())
