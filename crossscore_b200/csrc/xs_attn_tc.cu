@@ -27,8 +27,6 @@
 // xs_lse_merge combines (single-GPU small-batch split and the multi-GPU split-KV path).
 #include <stdlib.h>
 
-#include <type_traits>
-
 #include "xs_common.cuh"
 
 namespace xs {
@@ -735,314 +733,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Ping-pong variant: one CTA owns TWO adjacent 128-query tiles (A, B) of the same (batch, head, kv split) and its
-// softmax warps alternate between them block by block (A_0, B_0, A_1, B_1, ...).  While a warp works on tile B's
-// block, tile A's hand-over chain (P_A -> PV_A -> QK_A of the next block -> S_A) runs in the background and vice
-// versa, so the chain latency that paces the single-tile kernel is hidden behind a full block
-// of useful work; K/V tiles are loaded once for both tiles.  TMEM (256 columns): S_A [0,64), S_B [64,128) (one buffer
-// each, P aliases the upper half), O_A [128,192), O_B [192,256).  Shared memory: two Q tiles + a 4-stage K/V ring.
-// An odd last tile of a (batch, head) runs with an empty tile B (rows past Lq: zero-filled by TMA, never stored).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int ATP_ST = 4;
-constexpr uint32_t ATP_SMEM_BYTES = 2 * ATT_Q_BYTES + 2 * ATP_ST * ATT_KV_BYTES + 256 + 1024;
-
-template <int DQK_STEPS, int DV>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smQ = smem;                          // [2][128 rows][64 bf16]
-  uint8_t* smK = smem + 2 * ATT_Q_BYTES;
-  uint8_t* smV = smK + ATP_ST * ATT_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smV + ATP_ST * ATT_KV_BYTES);
-  const SmemBar bar0{smem_u32(bars)};
-  const SmemBar q_full = bar0 + 0;
-  const SmemBar q_empty = bar0 + 1;
-  const SmemBar kv_full = bar0 + 2;             // [ATP_ST]
-  const SmemBar kv_empty = kv_full + ATP_ST;    // [ATP_ST] both PVs of the block complete
-  const SmemBar s_full = kv_empty + ATP_ST;     // [2] per query tile
-  const SmemBar p_full = s_full + 2;            // [2]
-  const SmemBar o_full = p_full + 2;
-  const SmemBar o_empty = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * ATP_ST + 4 + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int s = 0; s < ATP_ST; ++s) {
-      mbar_init(kv_full + (s), 1);
-      mbar_init(kv_empty + (s), 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(s_full + (t), 1);
-      mbar_init(p_full + (t), 4);
-    }
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
-    fence_mbar_init();
-  }
-  if (warp == 5) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // `g` counts K/V blocks over the CTA's lifetime: ring slot g % ATP_ST (parity (g / ATP_ST) & 1); s_full[t] and
-  // p_full[t] complete once per block, parity g & 1; `it` counts tile pairs (q_*, o_* parities).
-  if (warp >= 4) reg_dealloc<ATT_REGS_CTRL>();
-  if (warp == 4) {
-    // ===================== TMA producer =====================
-    uint32_t g = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(tile, p);
-      const int q0 = 2 * t.q0;
-      const int b_kv = p.kv_shared ? 0 : t.b;
-      mbar_wait(q_empty, (it & 1) ^ 1);
-      if (elect_one_sync()) {
-        mbar_expect_tx(q_full, 2 * ATT_Q_BYTES);
-        tma_load_3d(smQ, &tmQ, q_full, t.h * 64, q0, t.b);
-        tma_load_3d(smQ + ATT_Q_BYTES, &tmQ, q_full, t.h * 64, q0 + 128, t.b);  // may lie past Lq: zero-filled
-      }
-      __syncwarp();
-      for (int j = 0; j < t.nkv; ++j, ++g) {
-        const uint32_t s = g % ATP_ST;
-        const int kv0 = t.kv_begin + j * ATT_BKV;
-        mbar_wait(kv_empty + (s), ((g / ATP_ST) & 1) ^ 1);
-        if (elect_one_sync()) {
-          mbar_expect_tx(kv_full + (s), 2 * ATT_KV_BYTES);
-          tma_load_3d(smK + s * ATT_KV_BYTES, &tmK, kv_full + (s), t.h * 64, kv0, b_kv);
-          tma_load_3d(smV + s * ATT_KV_BYTES, &tmV, kv_full + (s), t.h * 64, kv0, b_kv);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BKV, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DV, 0, 1);
-    const uint32_t tb = warp_uniform(tmem_base);
-    const uint32_t q_lo0 = umma_desc_lo(smem_u32(smQ), 16);
-    const uint32_t k_lo0 = umma_desc_lo(smem_u32(smK), 16);
-    const uint32_t v_lo0 = umma_desc_lo(smem_u32(smV), 1024);
-    // S_t(gg) = Q_t K_gg^T; `wait_k`: first use of the K slot by this warp; `last`: last QK of the pair (frees Q)
-    auto issue_qk = [&](uint32_t gg, int t, bool wait_k, bool last) {
-      const uint32_t s = gg % ATP_ST;
-      if (wait_k) mbar_wait(kv_full + (s), (gg / ATP_ST) & 1);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t q_lo = q_lo0 + t * (ATT_Q_BYTES >> 4);
-        const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
-#pragma unroll
-        for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(tb + t * 64, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        tc_commit(s_full + (t));
-        if (last) tc_commit(q_empty);
-      }
-      __syncwarp();
-    };
-    uint32_t g0 = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int nkv = decode_tile(tile, p).nkv;
-      mbar_wait(q_full, it & 1);
-      // S_A / S_B are free: the previous pair's PVs were issued before (in-order tensor pipe) and the softmax warps
-      // had read those logits before they arrived on p_full
-      issue_qk(g0, 0, true, false);
-      issue_qk(g0, 1, false, nkv == 1);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t g = g0 + j;
-        const uint32_t s = g % ATP_ST;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(p_full + (t), g & 1);
-          if (j == 0 && t == 0) mbar_wait(o_empty, (it & 1) ^ 1);  // previous pair's O_A, O_B have been read out
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
-            const uint32_t a_p = tb + t * 64 + 32;
-#pragma unroll
-            for (int k = 0; k < ATT_BKV / 16; ++k)
-              umma_ts_lh(tb + 128 + t * 64, a_p + k * 8, v_lo + k * 128, idesc_pv, (j | k) != 0 ? 1u : 0u);
-            if (t == 1) {
-              tc_commit(kv_empty + (s));  // K_g / V_g slot free; also "both PVs of block g complete" for the O rescale
-              if (j == nkv - 1) tc_commit(o_full);
-            }
-          }
-          __syncwarp();
-          if (j + 1 < nkv) issue_qk(g + 1, t, t == 0, t == 1 && j + 1 == nkv - 1);  // overwrites S_t behind PV_t(g)
-        }
-      }
-      g0 += nkv;
-    }
-  } else if (warp < 4) {
-    reg_alloc<ATT_REGS_SOFTMAX>();
-    // ===================== softmax (thread == query row of tile A and of tile B) =====================
-    const int q = warp;
-    const int row = q * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const float sl2 = p.scale_log2;
-    uint32_t g0 = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      int nkv, tail_valid;
-      {
-        const TileCoord t = decode_tile(tile, p);
-        nkv = t.nkv;
-        tail_valid = t.kv_end - t.kv_begin - (t.nkv - 1) * ATT_BKV;
-      }
-      // (m, l) is the state of the tile whose block is being processed, (m2, l2) the other tile's: swapped after
-      // every block, so the block code exists once per mask variant and the tile index is a run-time value
-      float m = -INFINITY, l = 0.f, m2 = -INFINITY, l2 = 0.f;
-      uint32_t va[32], vb[32];
-      if (lane == 0) mbar_wait(s_full + 0, g0 & 1);
-      __syncwarp();
-      tc_fence_after();
-      tmem_ld32(tmem_base + lane_off, va);  // S_A(g0) chunk A
-      const int nblk2 = 2 * nkv;
-
-      // block k of the interleaved sequence A_0, B_0, A_1, B_1, ...: tile T = k & 1, kv block j = k >> 1
-      auto block = [&](const int k, auto mask_tag) {
-        constexpr bool MASK = decltype(mask_tag)::value;
-        const uint32_t T = static_cast<uint32_t>(k) & 1u;
-        const int j = k >> 1;
-        const uint32_t g = g0 + j;
-        const uint32_t t_s = tmem_base + lane_off + T * 64;
-        const uint32_t t_o = tmem_base + lane_off + 128 + T * 64;
-        const uint32_t t_next = tmem_base + lane_off + (1u - T) * 64;       // S of the other tile
-        const bool has_next = k + 1 < nblk2;
-        const int valid = tail_valid;
-        uint32_t pka[16], pkb[16];
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        const float neg_m = -m;
-        tmem_ld_wait32(va);
-        tmem_ld32(t_s + 32, vb);
-        if constexpr (MASK) mask_tail(va, valid);
-        if (j > 0) exp_chunk<false>(va, sl2, neg_m, pka, acc0, acc1, 0);
-        tmem_ld_wait32(vb);
-        if (j > 0) tmem_st16(t_s + 32, pka);
-        if (has_next) {  // prefetch chunk A of the next block = the OTHER tile's (its chain ran during this block)
-          if (lane == 0) mbar_wait(s_full + (1u - T), (g0 + ((k + 1) >> 1)) & 1);
-          __syncwarp();
-          tc_fence_after();
-          tmem_ld32(t_next, va);
-        }
-        if constexpr (MASK) mask_tail(vb, valid - 32);
-        if (j > 0) exp_chunk<false>(vb, sl2, neg_m, pkb, acc0, acc1, 0);
-        float bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-        const bool need = (j == 0) || !(bsum <= ATT_SUM_LIMIT);
-        if (__any_sync(0xffffffffu, need)) {
-          if (has_next) tmem_ld_wait32(va);
-          tmem_ld32(t_s, va);
-          tmem_ld_wait32(va);
-          if constexpr (MASK) mask_tail(va, valid);
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(va[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(va[i + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(vb[i]));
-            mx3 = fmaxf(mx3, __uint_as_float(vb[i + 1]));
-          }
-          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
-          const float m_new = need ? fmaxf(mx, m) : m;
-          const float alpha = fast_exp2(m - m_new);
-          l *= alpha;
-          if (j > 0) {
-            // both PVs of the previous block complete (committed behind PV_B): O_T holds all earlier blocks
-            if (lane == 0) mbar_wait(kv_empty + ((g - 1) % ATP_ST), ((g - 1) / ATP_ST) & 1);
-            __syncwarp();
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < DV / 16; ++c) {
-              uint32_t v[16];
-              tmem_ld16(t_o + c * 16, v);
-              tmem_ld_wait16(v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st16(t_o + c * 16, v);
-            }
-          }
-          m = m_new;
-          acc0 = make_float2(0.f, 0.f);
-          acc1 = make_float2(0.f, 0.f);
-          tc_wait_st();
-          exp_chunk<false>(va, sl2, -m, pka, acc0, acc1, 0);
-          tmem_st16(t_s + 32, pka);
-          exp_chunk<false>(vb, sl2, -m, pkb, acc0, acc1, 0);
-          bsum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-          if (has_next) tmem_ld32(t_next, va);  // redo the prefetch
-        }
-        l += bsum;
-        tmem_st16(t_s + 48, pkb);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full + T);
-        // the other tile is next
-        const float tm = m, tl = l;
-        m = m2; l = l2; m2 = tm; l2 = tl;
-      };
-      for (int k = 0; k < nblk2 - 2; ++k) block(k, MaskNo{});
-      block(nblk2 - 2, MaskYes{});
-      block(nblk2 - 1, MaskYes{});
-      const float mA = m, lA = l, mB = m2, lB = l2;  // an even number of swaps: (m, l) is tile A's again
-      g0 += nkv;
-
-      // ---- epilogue: both O tiles out of TMEM, then O / l and log-sum-exp ----
-      if (lane == 0) mbar_wait(o_full, it & 1);
-      __syncwarp();
-      tc_fence_after();
-      const TileCoord t = decode_tile(tile, p);
-#pragma unroll
-      for (int T = 0; T < 2; ++T) {
-        const uint32_t t_o = tmem_base + lane_off + 128 + T * 64;
-        tmem_ld32(t_o, va);
-        if constexpr (DV == 64) tmem_ld32(t_o + 32, vb);
-        else tmem_ld16_lo(t_o + 32, vb);
-        tmem_ld_wait32(va);
-        tmem_ld_wait32(vb);
-        if (T == 1) {  // both accumulators are in registers / stored: the next pair's PV_0 may overwrite them
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(o_empty);
-        }
-        const float l = T == 0 ? lA : lB, m = T == 0 ? mA : mB;
-        const float inv = 1.0f / l;
-        const int row_g = 2 * t.q0 + T * 128 + row;
-        const long long o_off = static_cast<long long>(t.split) * p.o_split_stride +
-                                static_cast<long long>(t.b) * p.o_batch_stride +
-                                static_cast<long long>(row_g) * p.o_row_stride + static_cast<long long>(t.h) * DV;
-        if (row_g < p.Lq) {
-          if (p.o_is_f32) {
-            float* dst = reinterpret_cast<float*>(p.o) + o_off;
-            store_row_f32<0, 32>(dst, va, inv);
-            store_row_f32<0, DV - 32>(dst + 32, vb, inv);
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.o) + o_off;
-            store_row_bf16<0, 32>(dst, va, inv);
-            store_row_bf16<0, DV - 32>(dst + 32, vb, inv);
-          }
-          if (p.lse != nullptr) {
-            p.lse[static_cast<long long>(t.split) * p.lse_split_stride +
-                  (static_cast<long long>(t.b) * p.heads + t.h) * p.Lq + row_g] = (m + log2f(l)) * 0.6931471805599453f;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
 // Development aid (XS_ATTN_PROF=1): run the instrumented instantiation synchronously and print the average
 // clocks each softmax warp / MMA warp spent per phase (per CTA lifetime) to stderr.
 static int launch_attn_prof(int head_dim, dim3 grid, const CUtensorMap& tmQ, const CUtensorMap& tmK,
@@ -1147,27 +837,6 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
   if (dbg < 0) {
     const char* e = getenv("XS_ATTN_DBG");
     dbg = e ? atoi(e) : 0;
-  }
-  static int pair_mode = -1;
-  if (pair_mode < 0) {
-    const char* e = getenv("XS_ATTN_PAIR");
-    pair_mode = e ? atoi(e) : 0;
-  }
-  if (pair_mode && !operands_f16 && !prof && !dbg) {  // ping-pong: two query tiles per CTA
-    p.nq_tiles = (p.nq_tiles + 1) / 2;
-    p.n_tiles = p.nq_tiles * heads * B * nsplit;
-    dim3 grid2(p.n_tiles < max_ctas ? p.n_tiles : max_ctas);
-    if (head_dim == 64) {
-      auto kern = attn_tc_pair_kernel<4, 64>;
-      XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATP_SMEM_BYTES));
-      kern<<<grid2, ATT_THREADS, ATP_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-    } else {
-      auto kern = attn_tc_pair_kernel<3, 48>;
-      XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATP_SMEM_BYTES));
-      kern<<<grid2, ATT_THREADS, ATP_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-    }
-    XS_LAUNCH_CHECK();
-    return 0;
   }
   if (operands_f16) {
     if (prof) {  // phase clocks of the fp16 variant (XS_ATTN_PROF=1)
