@@ -54,7 +54,7 @@ def _build(objdir: str, LIB: str, defs, force: bool, verbose: bool) -> str:
             f.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    if rebuilt or not os.path.exists(LIB):
+    if rebuilt or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
         subprocess.check_call(cmd)
     return LIB

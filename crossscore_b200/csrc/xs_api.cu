@@ -82,7 +82,8 @@ int gemm_tc(const void*, int, const void*, int, const float*, void*, int, int, i
 int head_jigsaw_tc(const void*, int, const void*, int, const float*, float*, int, int, int, int, int, float, int,
                    cudaStream_t);
 int flash_attn_bf16_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long,
-                       long long, long long, long long, int, int, int, float, int, cudaStream_t);
+                       long long, long long, long long, int, int, int, float, cudaStream_t);
+void attn_set_optimistic(int);
 int gemm_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, cudaStream_t);
 int preprocess_u8(const uint8_t*, int, int, int, float*, int, int, const float*, cudaStream_t);
 size_t postprocess_workspace_bytes(int);
@@ -100,7 +101,7 @@ int rows_final_ln_pe(const float*, const void*, const float*, const float*, floa
                      int, int, int, int, cudaStream_t);
 int rows_im2col14(const float*, void*, int, int, int, int, int, cudaStream_t);
 int table_bilinear_ac(const float*, float*, int, int, int, int, int, cudaStream_t);
-int table_bicubic(const float*, float*, int, int, int, int, int, cudaStream_t);
+int table_bicubic(const float*, float*, int, int, int, int, int, float, float, cudaStream_t);
 int rows_lse_merge(const float*, const float*, void*, float*, int, int, int, int, int, long long, long long, int,
                    cudaStream_t);
 int rows_lse_merge_peers(const void* const*, long long, long long, void*, float*, int, int, int, int, int, int,
@@ -183,7 +184,12 @@ int xs_pe_resample_bilinear_ac(const float* table, float* out, int ih, int iw, i
 
 int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw, int oh, int ow, int channels,
                                   xs_stream_t stream) {
-  return table_bicubic(table, out, ih, iw, oh, ow, channels, static_cast<cudaStream_t>(stream));
+  return table_bicubic(table, out, ih, iw, oh, ow, channels, 0.f, 0.f, static_cast<cudaStream_t>(stream));
+}
+
+int xs_pos_embed_resample_bicubic_steps(const float* table, float* out, int ih, int iw, int oh, int ow, int channels,
+                                        float step_h, float step_w, xs_stream_t stream) {
+  return table_bicubic(table, out, ih, iw, oh, ow, channels, step_h, step_w, static_cast<cudaStream_t>(stream));
 }
 
 int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
@@ -215,10 +221,10 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
                   long long kv_row_stride, long long kv_batch_stride, int kv_shared, int nsplit, int o_is_f32,
                   float scale, int dtype, xs_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == XS_BF16 || dtype == XS_F16) {
-    XS_CHECK_ARG(head_slot == 64, "flash_attn(16-bit): head_slot must be 64, got %d", head_slot);
+  if (dtype == XS_BF16) {
+    XS_CHECK_ARG(head_slot == 64, "flash_attn(bf16): head_slot must be 64, got %d", head_slot);
     return flash_attn_bf16_tc(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, q_row_stride, q_batch_stride,
-                              kv_row_stride, kv_batch_stride, kv_shared, nsplit, o_is_f32, scale, dtype == XS_F16, st);
+                              kv_row_stride, kv_batch_stride, kv_shared, nsplit, o_is_f32, scale, st);
   }
   if (dtype == XS_F32) {
     XS_CHECK_ARG(o_is_f32, "flash_attn(fp32): output must be fp32");
@@ -229,6 +235,8 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
   set_last_error("flash_attn: unknown dtype %d", dtype);
   return -1;
 }
+
+void xs_attn_set_optimistic(int enable) { attn_set_optimistic(enable); }
 
 int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float* lse_out, int n_parts, int B, int Lq,
                  int heads, int head_dim, long long o_part_stride, long long lse_part_stride, int dtype,

@@ -276,11 +276,11 @@ __device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
   w[3] = c2(2.f - t);
 }
 // bicubic (A=-0.75), align_corners=False, border-clamped taps ($SP/.../modeling_dinov2.py:86-91)
+// sy / sx: source step per output pixel.  F.interpolate(size=...) uses in/out; F.interpolate(scale_factor=s) uses 1/s
+// (ATen area_pixel_compute_scale), which is what transformers 4.33.3 -- the reference's pinned version -- asks for.
 __global__ void bicubic_kernel(const float* __restrict__ in, float* __restrict__ out, int ih, int iw, int oh, int ow,
-                               int ch) {
+                               int ch, float sy, float sx) {
   const long long total = static_cast<long long>(oh) * ow * ch;
-  const float sy = static_cast<float>(ih) / static_cast<float>(oh);
-  const float sx = static_cast<float>(iw) / static_cast<float>(ow);
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % ch);
@@ -487,9 +487,14 @@ int table_bilinear_ac(const float* in, float* out, int ih, int iw, int oh, int o
   return 0;
 }
 
-int table_bicubic(const float* in, float* out, int ih, int iw, int oh, int ow, int ch, cudaStream_t stream) {
+int table_bicubic(const float* in, float* out, int ih, int iw, int oh, int ow, int ch, float step_h, float step_w,
+                  cudaStream_t stream) {
   XS_CHECK_ARG(ih > 0 && iw > 0 && oh > 0 && ow > 0 && ch > 0, "pos_resample: bad dims");
-  bicubic_kernel<<<grid_for(static_cast<long long>(oh) * ow * ch), 256, 0, stream>>>(in, out, ih, iw, oh, ow, ch);
+  XS_CHECK_ARG(step_h >= 0.f && step_w >= 0.f, "pos_resample: negative source step");
+  const float sy = step_h > 0.f ? step_h : static_cast<float>(ih) / static_cast<float>(oh);
+  const float sx = step_w > 0.f ? step_w : static_cast<float>(iw) / static_cast<float>(ow);
+  bicubic_kernel<<<grid_for(static_cast<long long>(oh) * ow * ch), 256, 0, stream>>>(in, out, ih, iw, oh, ow, ch, sy,
+                                                                                     sx);
   XS_LAUNCH_CHECK();
   return 0;
 }

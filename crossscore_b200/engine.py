@@ -44,15 +44,33 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+POS_INTERP_MODES = ("scale_factor", "size")
+
+
+def pos_interp_steps(mode: str, g: int, ph: int, pw: int):
+    """Source step per output pixel of the DINOv2 position-embedding resample (0.0 = g / out, the size= form).
+
+    "scale_factor": transformers 4.33.3, the version the reference pins (environment.yaml:340), calls
+    F.interpolate(scale_factor=((ph + 0.1) / g, (pw + 0.1) / g)); ATen then maps output to source coordinates with
+    1 / scale_factor (computed in double, used in fp32).  "size": transformers >= 4.4x pass size=(ph, pw)
+    ($SP/transformers/models/dinov2/modeling_dinov2.py:86-91), i.e. g / ph."""
+    if mode == "size":
+        return 0.0, 0.0
+    return 1.0 / ((ph + 0.1) / g), 1.0 / ((pw + 0.1) / g)
+
+
 class PackedWeights:
     """Kernel-friendly copies of the reference state_dict (built once per device / precision)."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], device, precision: str, do_self_attn: bool = True,
-                 fold_qscale: bool = False):
+                 fold_qscale: bool = False, pos_interp: str = "scale_factor"):
         """fold_qscale: multiply the query projections by softmax_scale * log2(e) (in fp32, before rounding), so the
-        attention kernel's logits are already in the log2 domain (fp16-logit attention: scale_log2 == 1 exactly and
-        the fp16 accumulators hold small numbers)."""
+        attention kernel's logits are already in the log2 domain and its softmax needs no multiply per logit
+        (the bf16 product mode; the fp32 parity mode keeps the reference's operation order)."""
         assert precision in ("bf16", "fp32")
+        if pos_interp not in POS_INTERP_MODES:
+            raise ValueError(f"pos_interp must be one of {POS_INTERP_MODES}, got {pos_interp!r}")
+        self.pos_interp = pos_interp
         self.precision = precision
         self.fold_qscale = fold_qscale
         LOG2E = 1.4426950408889634
@@ -154,7 +172,9 @@ class PackedWeights:
             else:
                 pos = torch.empty(1 + ph * pw, C, device=dev, dtype=torch.float32)
                 pos[0] = self.pos[0]
-                call("xs_pos_embed_resample_bicubic", _ptr(self.pos[1:]), _ptr(pos[1:]), g, g, ph, pw, C, stream)
+                step_h, step_w = pos_interp_steps(self.pos_interp, g, ph, pw)
+                call("xs_pos_embed_resample_bicubic_steps", _ptr(self.pos[1:]), _ptr(pos[1:]), g, g, ph, pw, C,
+                     step_h, step_w, stream)
             pe_h, pe_w = self.pe_table.shape[:2]
             if ph == pe_h and pw == pe_w:  # positional_encoding.py:51-56 shortcut
                 pe = self.pe_table.reshape(ph * pw, C)
@@ -169,20 +189,17 @@ class Engine:
     """Runs the forward on one GPU.  One Engine per (module, device, precision)."""
 
     def __init__(self, sd, device, precision="bf16", do_self_attn=True, do_short_cut=True,
-                 use_tanh=False, power=1.0):
+                 use_tanh=False, power=1.0, pos_interp="scale_factor"):
         _lib.load()
         with torch.cuda.device(device):
             call("xs_device_check")
-        # XS_ATTN_F16=1 (bf16 product mode only): attention on fp16 operands with fp16 logit accumulators and a
-        # packed-half softmax.  Parity-tested, but measured no faster than the bf16 / fp32-logit kernel (both end up
-        # bound by the MUFU, DESIGN.md section 4), so it is opt-in.
-        self.attn_f16 = precision == "bf16" and os.environ.get("XS_ATTN_F16", "0") == "1"
-        self.w = PackedWeights(sd, device, precision, do_self_attn, fold_qscale=self.attn_f16)
+        self.w = PackedWeights(sd, device, precision, do_self_attn, fold_qscale=precision == "bf16",
+                               pos_interp=pos_interp)
         self.device = device
         self.dt = self.w.dt
         self.adtype = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.qdtype = torch.float16 if self.attn_f16 else self.adtype   # q / k / v and the decoder K/V cache
-        self.attn_dt = DT_F16 if self.attn_f16 else self.dt
+        self.qdtype = self.adtype   # q / k / v and the decoder K/V cache
+        self.attn_dt = self.dt
         self.do_self_attn, self.do_short_cut = do_self_attn, do_short_cut
         self.use_tanh, self.power = bool(use_tanh), float(power)
         self._ws = {}
@@ -341,9 +358,10 @@ class Engine:
                 self._ln(h, d, h, Ln["ln1_g"], Ln["ln1_b"], DINO_EPS, y, None, R, st)  # h += d ; y = LN1_{l+1}(h)
         return h, (None if fused else d), I, P
 
-    def features(self, query_img, ref_imgs, st, want_mem=True):
+    def features(self, query_img, ref_imgs, st, want_mem=True, pe_table=None):
         """DINOv2 + final LN + CLS drop + PE.  query_img (B,3,H,W) or None, ref_imgs (B,N,3,H,W) or None.
-        Returns xq32 (B*P,C) fp32 and mem (B*N*P,C) AT (None where not requested)."""
+        Returns xq32 (B*P,C) fp32 and mem (B*N*P,C) AT (None where not requested).
+        pe_table (P, C) fp32 replaces the resampled multi-view PE (get_featmaps passes zeros)."""
         w = self.w
         groups, nq = [], 0
         if query_img is not None:
@@ -358,41 +376,18 @@ class Engine:
         ph, pw = H // PATCH, Wd // PATCH
         P = ph * pw
         _, pe = w.tables(ph, pw, st)
+        if pe_table is not None:
+            assert pe_table.shape == (P, C) and pe_table.dtype == torch.float32 and pe_table.is_contiguous()
+            pe = pe_table
         xq32 = self._buf("xq32", (nq * P, C), torch.float32) if nq else None
         mem = self._buf("mem", (nr * P, C), self.adtype) if nr and want_mem else None
         es = self.adtype.itemsize
-        # The images are independent through the whole backbone, so it runs CHUNK BY CHUNK (all 12 layers for a few
-        # images at a time): the per-layer intermediates (y, qkv, att, g: 22 bytes per residual element) of a chunk
-        # then fit in the 126 MB L2 and producer -> consumer traffic stays on chip instead of going through HBM,
-        # which otherwise co-bounds the K = 384 GEMMs and the LayerNorms.
-        total = nq + nr
-        chunk = self.chunk_images(P) if self.dt == DT_BF16 else total
         flat = [g.reshape(-1, *g.shape[-3:]) for g in groups]
-        sizes = [int(f.shape[0]) for f in flat]
-        for i0 in range(0, total, chunk):
-            i1 = min(total, i0 + chunk)
-            parts, base = [], 0
-            for f, n in zip(flat, sizes):  # slices of the (query..., refs...) image list that fall into [i0, i1)
-                lo, hi = max(i0, base), min(i1, base + n)
-                if lo < hi:
-                    parts.append(f[lo - base:hi - base])
-                base += n
-            h, d, I, _ = self.backbone(parts, st)
-            q_here = max(0, min(i1, nq) - i0)                      # query images in this chunk (they come first)
-            xq_dst = xq32[i0 * P:] if q_here else None
-            mem_dst = mem[max(i0, nq) * P - nq * P:] if (mem is not None and i1 > nq) else None
-            with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + (es if d is not None else 0) + es)):
-                call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS,
-                     _ptr(pe), _ptr(xq_dst), None, _ptr(mem_dst), I, q_here, P, self.dt, st)
+        h, d, I, _ = self.backbone(flat, st)
+        with self._op("final_ln_pe", 0.0, I * (P + 1) * C * (4 + (es if d is not None else 0) + es)):
+            call("xs_final_ln_drop_cls_add_pe", _ptr(h), _ptr(d), _ptr(w.lnf_g), _ptr(w.lnf_b), DINO_EPS,
+                 _ptr(pe), _ptr(xq32), None, _ptr(mem), I, nq, P, self.dt, st)
         return xq32, mem
-
-    def chunk_images(self, P: int) -> int:
-        """Images per backbone chunk (bf16 mode).  XS_CHUNK_IMAGES overrides (0 = no chunking)."""
-        env = os.environ.get("XS_CHUNK_IMAGES")
-        if env is not None:
-            n = int(env)
-            return n if n > 0 else 1 << 30
-        return 1 << 30
 
     def project_kv(self, mem, st, out=None):
         """K/V of both decoder layers for reference tokens mem (rows, C) -> (rows, 4E)."""

@@ -40,12 +40,19 @@ class _Tree(nn.Module):
 class CrossScoreNet(nn.Module):
     """B200-native CrossScore model (inference).  See module docstring.
 
-    Extra keyword (not in the reference): ``precision`` = "bf16" (tcgen05 tensor-core path, default) or
-    "fp32" (parity mode, max-abs <= 1e-4 vs the fp32 reference).
+    Extra keywords (not in the reference): ``precision`` = "bf16" (tcgen05 tensor-core path, default) or
+    "fp32" (parity mode, max-abs <= 1e-4 vs the fp32 reference).  ``dinov2_pos_interp`` selects how the DINOv2
+    position table is resampled for inputs other than 518x518: "scale_factor" (default) reproduces transformers
+    4.33.3, the version the reference pins (environment.yaml:340: ``F.interpolate(scale_factor=(h+0.1)/37)``);
+    "size" reproduces transformers >= 4.4x (``F.interpolate(size=(h, w))``).  The two differ by up to ~0.2 in table
+    entries on non-square grids, so pick the one the checkpoint's own stack used.
     """
 
-    def __init__(self, cfg=None, precision: str = "bf16"):
+    def __init__(self, cfg=None, precision: str = "bf16", dinov2_pos_interp: str = "scale_factor"):
         super().__init__()
+        if dinov2_pos_interp not in ("scale_factor", "size"):
+            raise ValueError(f"dinov2_pos_interp must be 'scale_factor' or 'size', got {dinov2_pos_interp!r}")
+        self.dinov2_pos_interp = dinov2_pos_interp
         self.cfg = cfg if cfg is not None else default_cfg()
         m = self.cfg.model
         if not m.do_reference_cross:
@@ -75,28 +82,38 @@ class CrossScoreNet(nn.Module):
             top, rest = name.split(".", 1)
             self._modules[top].attach(rest, init[name])
         self._engines = {}
-        self._version = 0
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh())
 
     # ---- weights ---------------------------------------------------------------------------------
-    def _invalidate(self):
-        self._version += 1
+    def refresh(self):
+        """Drop the packed device copies of the weights; the next forward repacks them from the parameters."""
         self._engines.clear()
 
     def _apply(self, fn, *a, **k):  # .to() / .cuda() move the source parameters; repack lazily
         out = super()._apply(fn, *a, **k)
-        self._invalidate()
+        self.refresh()
         return out
+
+    def _weights_stamp(self):
+        """Cheap fingerprint of the source parameters: in-place edits (``p.data.copy_()``, ``p.data = ...``) bump
+        ``_version`` or change ``data_ptr``, so the packed copies are rebuilt instead of going stale silently."""
+        stamp = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            stamp = (stamp * 1000003 + t._version * 7919 + t.data_ptr()) & 0xFFFFFFFFFFFF
+        return stamp
 
     def _engine(self, device):
         from .engine import Engine
         key = (str(device), self.precision)
-        if key not in self._engines:
-            self._engines[key] = Engine(self.state_dict(), device, self.precision,
-                                        do_self_attn=bool(self.cfg.model.decoder_do_self_attn),
-                                        do_short_cut=bool(self.cfg.model.decoder_do_short_cut),
-                                        use_tanh=self._use_tanh, power=self._power)
-        return self._engines[key]
+        stamp = self._weights_stamp()
+        cur = self._engines.get(key)
+        if cur is None or cur[0] != stamp:
+            cur = (stamp, Engine(self.state_dict(), device, self.precision,
+                                 do_self_attn=bool(self.cfg.model.decoder_do_self_attn),
+                                 do_short_cut=bool(self.cfg.model.decoder_do_short_cut),
+                                 use_tanh=self._use_tanh, power=self._power, pos_interp=self.dinov2_pos_interp))
+            self._engines[key] = cur
+        return cur[1]
 
     # ---- reference API ---------------------------------------------------------------------------
     @torch.no_grad()
@@ -126,19 +143,11 @@ class CrossScoreNet(nn.Module):
         st = torch.cuda.current_stream(query_img.device).cuda_stream
         B, _, H, W = query_img.shape
         P = (H // 14) * (W // 14)
-        saved = eng.w._tables.copy()
-        try:
-            # same kernels with a zero PE table
-            pos, _ = eng.w.tables(H // 14, W // 14, st)
-            eng.w._tables[(H // 14, W // 14)] = (pos, torch.zeros(P, 384, device=query_img.device))
-            refs = None if ref_cross_imgs is None else ref_cross_imgs.contiguous()
-            xq32, mem = eng.features(query_img.contiguous(), refs, st)
-            out = {"query": xq32.view(B, P, 384).clone(),
-                   "ref_cross": None if mem is None else mem.float().view(B, -1, 384).clone()}
-        finally:
-            eng.w._tables.clear()
-            eng.w._tables.update(saved)
-        return out
+        refs = None if ref_cross_imgs is None else ref_cross_imgs.contiguous()
+        zero_pe = torch.zeros(P, 384, device=query_img.device)  # same kernels, PE table of zeros
+        xq32, mem = eng.features(query_img.contiguous(), refs, st, pe_table=zero_pe)
+        return {"query": xq32.view(B, P, 384).clone(),
+                "ref_cross": None if mem is None else mem.float().view(B, -1, 384).clone()}
 
     @staticmethod
     def _check_inputs(query_img, ref_cross_imgs):
@@ -166,10 +175,14 @@ def strip_lightning_prefix(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tenso
     return dict(sd)
 
 
-def load_checkpoint(net: CrossScoreNet, path_or_dict, strict: bool = True):
-    """Load ``CrossScore-v1.0.0.ckpt`` (Lightning dict with "state_dict") or a bare state_dict."""
+def load_checkpoint(net: CrossScoreNet, path_or_dict, strict: bool = True, allow_pickle: bool = False):
+    """Load ``CrossScore-v1.0.0.ckpt`` (Lightning dict with "state_dict") or a bare state_dict.
+
+    Files are read with ``weights_only=True`` (tensors and plain containers: what a Lightning checkpoint saved with
+    ``save_hyperparameters(OmegaConf.to_container(...))`` holds, task/core.py:170).  ``allow_pickle=True`` opts into
+    full unpickling, which executes code from the file: only for checkpoints you trust."""
     obj = path_or_dict
     if isinstance(obj, (str, bytes)) or hasattr(obj, "__fspath__"):
-        obj = torch.load(obj, map_location="cpu", weights_only=False)
+        obj = torch.load(obj, map_location="cpu", weights_only=not allow_pickle)
     sd = obj["state_dict"] if isinstance(obj, dict) and "state_dict" in obj else obj
     return net.load_state_dict(strip_lightning_prefix(sd), strict=strict)

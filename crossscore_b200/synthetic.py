@@ -107,21 +107,41 @@ def _scale_offset(name: str) -> Tuple[float, float]:
     raise KeyError(name)
 
 
+OUTLIER_CHANNELS = (5, 133, 301)
+
+
 def make_state_dict(seed: int = 1, pe_h: int = 40, pe_w: int = 40, do_self_attn: bool = True,
-                    lightning_prefix: bool = False) -> "OrderedDict[str, torch.Tensor]":
+                    lightning_prefix: bool = False, variant: str = "benign") -> "OrderedDict[str, torch.Tensor]":
     """Seeded fp32 state_dict with the reference schema.  ``lightning_prefix`` adds the
-    ``model.`` prefix a Lightning checkpoint carries (task/core.py:173)."""
+    ``model.`` prefix a Lightning checkpoint carries (task/core.py:173).
+
+    variant "outlier" mimics what trained DINOv2 weights do to a bf16 pipeline: a few
+    residual channels carry activations ~100x the rest (the rows of the patch projection, of every fc2 and of the
+    position table that write channels OUTLIER_CHANNELS are scaled up), LayerScale spreads up to 1.5, and the
+    query / key projections are 1.6x wider so attention logits reach +-35."""
+    if variant not in ("benign", "outlier"):
+        raise ValueError(f"unknown weight variant {variant!r}")
     sd = OrderedDict()
     for idx, (name, shape) in enumerate(state_dict_spec(pe_h, pe_w, do_self_attn)):
         if name == "img_mean_std":
             t = torch.tensor([*IMAGENET_MEAN, *IMAGENET_STD], dtype=torch.float32)
         elif name.endswith("lambda1"):
             g = torch.Generator().manual_seed(seed * 1000003 + idx)
-            t = 0.05 + 0.95 * torch.rand(shape, generator=g, dtype=torch.float32)
+            t = 0.05 + (1.45 if variant == "outlier" else 0.95) * torch.rand(shape, generator=g, dtype=torch.float32)
         else:
             g = torch.Generator().manual_seed(seed * 1000003 + idx)
             s, o = _scale_offset(name)
             t = torch.randn(shape, generator=g, dtype=torch.float32) * s + o
+            if variant == "outlier":
+                ch = list(OUTLIER_CHANNELS)
+                if "patch_embeddings.projection.weight" in name:
+                    t[ch] *= 40.0
+                elif name.endswith("position_embeddings"):
+                    t[..., ch] *= 40.0
+                elif "mlp.fc2.weight" in name:
+                    t[ch] *= 25.0
+                elif "attention.attention.query.weight" in name or "attention.attention.key.weight" in name:
+                    t *= 1.6
         sd[("model." if lightning_prefix else "") + name] = t
     return sd
 

@@ -95,6 +95,11 @@ int xs_pe_resample_bilinear_ac(const float* table, float* out, int ih, int iw, i
 /* DINOv2 pos-emb grid (ih,iw,C) -> (oh,ow,C), bicubic align_corners=False (modeling_dinov2.py:57-95) */
 int xs_pos_embed_resample_bicubic(const float* table, float* out, int ih, int iw, int oh, int ow, int channels,
                                   xs_stream_t stream);
+/* Same with explicit source steps per output pixel (0 = ih/oh resp. iw/ow).  transformers 4.33.3 -- the version the
+ * reference pins (environment.yaml:340) -- calls F.interpolate(scale_factor=((oh+0.1)/ih, (ow+0.1)/iw)), for which
+ * ATen steps by 1/scale_factor = ih/(oh+0.1); newer transformers pass size=, i.e. ih/oh. */
+int xs_pos_embed_resample_bicubic_steps(const float* table, float* out, int ih, int iw, int oh, int ow, int channels,
+                                        float step_h, float step_w, xs_stream_t stream);
 
 /* K3,K5-K7,K9-K11  out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N])   (torch.nn.Linear everywhere on the path)
  *     dtype = operand type (BF16 / TF32 tensor cores, F32 SIMT); out_dtype = BF16 or F32.
@@ -122,6 +127,11 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
                   int Lk, int head_dim, int head_slot, long long q_row_stride, long long q_batch_stride,
                   long long kv_row_stride, long long kv_batch_stride, int kv_shared, int nsplit, int o_is_f32,
                   float scale, int dtype, xs_stream_t stream);
+
+/*     The bf16 kernel's first pass takes 2^(logit * log2 e) with no running maximum (exact while the row sums stay
+ *     inside [2^-80, 2^100]); tiles that leave that range are redone with the online softmax in the same launch.
+ *     enable = 0 sends every tile through the online-softmax pass (process-wide; default 1). */
+void xs_attn_set_optimistic(int enable);
 
 /* C2  split-KV merge: LSE = log sum_r exp(LSE_r), O = sum_r exp(LSE_r - LSE) O_r  (no reference counterpart;
  *     identity in SURVEY.md appendix B-10).  Parts may come from local splits or an NCCL all-gather:

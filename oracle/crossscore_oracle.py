@@ -109,15 +109,17 @@ def _cubic_coeffs(t: torch.Tensor, A: float = -0.75):
     return [c2(t + 1.0), c1(t), c1(1.0 - t), c2(2.0 - t)]
 
 
-def bicubic_resize_ac_false(table: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+def bicubic_resize_ac_false(table: torch.Tensor, oh: int, ow: int, step_h=None, step_w=None) -> torch.Tensor:
     """(ih, iw, C) -> (oh, ow, C), bicubic, align_corners=False, border-clamped taps.
     Restates F.interpolate(mode="bicubic", align_corners=False, size=...) used by
-    $SP/transformers/models/dinov2/modeling_dinov2.py:86-91 (computed in fp32 there)."""
+    $SP/transformers/models/dinov2/modeling_dinov2.py:86-91 (computed in fp32 there).
+    step_h / step_w: source step per output pixel when the caller passed scale_factor= instead of size=
+    (ATen area_pixel_compute_scale: 1 / scale_factor); None = ih / oh."""
     ih, iw, _ = table.shape
     dt = table.dtype
 
-    def axis(o, i):
-        scale = i / o
+    def axis(o, i, step):
+        scale = i / o if step is None else step
         src = (torch.arange(o, dtype=dt) + 0.5) * scale - 0.5
         fl = torch.floor(src)
         t = src - fl
@@ -125,8 +127,8 @@ def bicubic_resize_ac_false(table: torch.Tensor, oh: int, ow: int) -> torch.Tens
         taps = [torch.clamp(idx + k, 0, i - 1) for k in (-1, 0, 1, 2)]
         return taps, _cubic_coeffs(t)
 
-    ty, wy = axis(oh, ih)
-    tx, wx = axis(ow, iw)
+    ty, wy = axis(oh, ih, step_h)
+    tx, wx = axis(ow, iw, step_w)
     out = torch.zeros(oh, ow, table.shape[2], dtype=dt)
     for a in range(4):
         rows = table[ty[a]]  # (oh, iw, C)
@@ -163,15 +165,29 @@ def bilinear_resize_ac_true(table: torch.Tensor, oh: int, ow: int) -> torch.Tens
     return top * (1 - ty)[:, None, None] + bot * ty[:, None, None]
 
 
-def dinov2_pos_table(sd: Dict[str, torch.Tensor], H: int, W: int, dt) -> torch.Tensor:
+# How Dinov2Embeddings.interpolate_pos_encoding resamples the 37x37 position grid for inputs other than 518x518:
+#   "scale_factor": transformers 4.33.3, the version the reference pins (environment.yaml:340) --
+#       F.interpolate(scale_factor=((ph + 0.1) / 37, (pw + 0.1) / 37), mode="bicubic", align_corners=False);
+#       with an explicit scale_factor ATen steps the source coordinate by 1 / scale_factor = 37 / (ph + 0.1).
+#       (4.33.3 is not installed here: this follows its published source, and tests pin the arithmetic against
+#       F.interpolate(scale_factor=...) itself.)
+#   "size": transformers >= 4.4x, incl. the 5.5.0 of this container ($SP/.../modeling_dinov2.py:86-91) --
+#       F.interpolate(size=(ph, pw)), i.e. a step of 37 / ph.
+POS_INTERP = "scale_factor"
+
+
+def dinov2_pos_table(sd: Dict[str, torch.Tensor], H: int, W: int, dt, pos_interp: Optional[str] = None) -> torch.Tensor:
     """Dinov2Embeddings.interpolate_pos_encoding ($SP/.../modeling_dinov2.py:57-95)."""
+    mode = pos_interp or POS_INTERP
+    assert mode in ("scale_factor", "size"), mode
     pos = sd["backbone.embeddings.position_embeddings"][0]  # (1+37*37, C)
     ph, pw = H // PATCH, W // PATCH
     if ph * pw == pos.shape[0] - 1 and H == W:
         return pos.to(dt)
     g = int(round(math.sqrt(pos.shape[0] - 1)))
+    steps = (None, None) if mode == "size" else (1.0 / ((ph + 0.1) / g), 1.0 / ((pw + 0.1) / g))
     # the library interpolates in fp32 whatever the model dtype (:86-91)
-    grid = bicubic_resize_ac_false(pos[1:].reshape(g, g, -1).to(torch.float32).to(dt), ph, pw)
+    grid = bicubic_resize_ac_false(pos[1:].reshape(g, g, -1).to(torch.float32).to(dt), ph, pw, *steps)
     return torch.cat([pos[:1].to(dt), grid.reshape(ph * pw, -1)], dim=0)
 
 
@@ -187,7 +203,7 @@ def multiview_pe_table(sd: Dict[str, torch.Tensor], H: int, W: int, dt) -> torch
 # ----------------------------------------------------------------------------------------
 # the path
 # ----------------------------------------------------------------------------------------
-def dinov2_features(sd: Dict[str, torch.Tensor], imgs: torch.Tensor, dt=torch.float64) -> torch.Tensor:
+def dinov2_features(sd: Dict[str, torch.Tensor], imgs: torch.Tensor, dt=torch.float64, pos_interp=None) -> torch.Tensor:
     """Dinov2Model(pixel_values).last_hidden_state: (I,3,H,W) -> (I, 1+P, C).
     $SP/transformers/models/dinov2/modeling_dinov2.py:97-116 (embeddings), :141-149 (patch
     conv k=s=14), :203-234 (attention, 6 heads x 64, scale 1/8), :249-252 (out dense),
@@ -202,7 +218,7 @@ def dinov2_features(sd: Dict[str, torch.Tensor], imgs: torch.Tensor, dt=torch.fl
     wpe = g("embeddings.patch_embeddings.projection.weight").reshape(HIDDEN, -1)
     tok = linear(patches, wpe, g("embeddings.patch_embeddings.projection.bias"))
     cls = g("embeddings.cls_token").expand(I, -1, -1)
-    h = torch.cat([cls, tok], dim=1) + dinov2_pos_table(sd, H, W, dt)[None]
+    h = torch.cat([cls, tok], dim=1) + dinov2_pos_table(sd, H, W, dt, pos_interp)[None]
     d = HIDDEN // DINO_HEADS
     for l in range(DINO_LAYERS):
         p = f"encoder.layer.{l}."
@@ -228,13 +244,13 @@ def dinov2_features(sd: Dict[str, torch.Tensor], imgs: torch.Tensor, dt=torch.fl
     return layer_norm(h, g("layernorm.weight"), g("layernorm.bias"), DINO_EPS)
 
 
-def get_featmaps(sd, query_img, ref_imgs, dt=torch.float64):
+def get_featmaps(sd, query_img, ref_imgs, dt=torch.float64, pos_interp=None):
     """CrossScoreNet.get_featmaps (task/core.py:119-161): one backbone pass over
     cat([query, refs]); drop CLS (:142); split query / refs (:146-153)."""
     B, _, H, W = query_img.shape
     N = ref_imgs.shape[1]
     allv = torch.cat([query_img[:, None], ref_imgs], dim=1).reshape(B * (1 + N), 3, H, W)
-    f = dinov2_features(sd, allv, dt)[:, 1:]
+    f = dinov2_features(sd, allv, dt, pos_interp)[:, 1:]
     P = f.shape[1]
     f = f.view(B, 1 + N, P, HIDDEN)
     return f[:, 0], f[:, 1:].reshape(B, N * P, HIDDEN)
@@ -295,13 +311,13 @@ def head_and_jigsaw(sd, x, ph, pw, metric_type="ssim", metric_min=0, power_facto
 
 def crossscore_forward(sd, query_img, ref_imgs, *, need_attn_weights=False, head_id=0,
                        do_self_attn=True, do_short_cut=True, metric_type="ssim", metric_min=0,
-                       power_factor="default", dt=torch.float64):
+                       power_factor="default", dt=torch.float64, pos_interp=None):
     """CrossScoreNet.forward with norm_img=False (task/core.py:58-117) ->
     {"score_map_ref_cross": (B, 14*ph, 14*pw), "attn_weights_map_ref_cross": None | (B,ph,pw,N,ph,pw)}."""
     B, _, H, W = query_img.shape
     N = ref_imgs.shape[1]
     ph, pw = H // PATCH, W // PATCH
-    fq, fr = get_featmaps(sd, query_img, ref_imgs, dt)
+    fq, fr = get_featmaps(sd, query_img, ref_imgs, dt, pos_interp)
     pe = multiview_pe_table(sd, H, W, dt)
     fq = fq + pe[None]
     fr = (fr.view(B, N, ph * pw, HIDDEN) + pe[None, None]).reshape(B, N * ph * pw, HIDDEN)

@@ -57,13 +57,44 @@ def boot_reference():
     return core
 
 
+def legacy_interpolate_pos_encoding(self, embeddings, height, width):
+    """Dinov2Embeddings.interpolate_pos_encoding as published in transformers 4.33.3 -- the version the reference
+    pins (environment.yaml:340), not installable here -- restated so that goldens of the pinned stack's behaviour
+    exist next to those of this container's 5.5.0 (the only difference: scale_factor=(h+0.1)/37 instead of size=)."""
+    import math
+    num_patches = embeddings.shape[1] - 1
+    num_positions = self.position_embeddings.shape[1] - 1
+    if num_patches == num_positions and height == width:
+        return self.position_embeddings
+    class_pos_embed = self.position_embeddings[:, 0]
+    patch_pos_embed = self.position_embeddings[:, 1:]
+    dim = embeddings.shape[-1]
+    height = height // self.config.patch_size
+    width = width // self.config.patch_size
+    height, width = height + 0.1, width + 0.1
+    g = int(math.sqrt(num_positions))
+    patch_pos_embed = patch_pos_embed.reshape(1, g, g, dim).permute(0, 3, 1, 2)
+    patch_pos_embed = torch.nn.functional.interpolate(
+        patch_pos_embed, scale_factor=(height / math.sqrt(num_positions), width / math.sqrt(num_positions)),
+        mode="bicubic", align_corners=False)
+    if int(height) != patch_pos_embed.shape[-2] or int(width) != patch_pos_embed.shape[-1]:
+        raise ValueError("Width or height does not match with the interpolated position embeddings")
+    patch_pos_embed = patch_pos_embed.permute(0, 2, 3, 1).view(1, -1, dim)
+    return torch.cat((class_pos_embed.unsqueeze(0), patch_pos_embed), dim=1)
+
+
 def run_case(core, name, B, N, H, W, seed_w=1, seed_x=0, need_w=False, head_id=0, subsample=None,
-             cfg_over=None, pe=(40, 40), save_feats=False):
+             cfg_over=None, pe=(40, 40), save_feats=False, variant="benign", pos_interp="size"):
     cfg = default_cfg(**(cfg_over or {}))
     cfg.model.pos_enc.multi_view.h, cfg.model.pos_enc.multi_view.w = pe
     do_sa = cfg.model.decoder_do_self_attn
+    from transformers.models.dinov2 import modeling_dinov2 as MD
+    if not hasattr(MD, "_stock_interp"):
+        MD._stock_interp = MD.Dinov2Embeddings.interpolate_pos_encoding
+    MD.Dinov2Embeddings.interpolate_pos_encoding = (legacy_interpolate_pos_encoding if pos_interp == "scale_factor"
+                                                    else MD._stock_interp)
     net = core.CrossScoreNet(cfg).eval()
-    sd = make_state_dict(seed_w, pe_h=pe[0], pe_w=pe[1], do_self_attn=do_sa)
+    sd = make_state_dict(seed_w, pe_h=pe[0], pe_w=pe[1], do_self_attn=do_sa, variant=variant)
     missing = net.load_state_dict(sd, strict=True)
     q, r = make_inputs(B, N, H, W, seed_x)
     with torch.inference_mode():
@@ -86,6 +117,10 @@ def run_case(core, name, B, N, H, W, seed_w=1, seed_x=0, need_w=False, head_id=0
         rec["feat_ref"] = feats["ref_cross"].float().numpy()
     if cfg_over:
         rec["cfg_over"] = np.array(repr(sorted(cfg_over.items())))
+    if variant != "benign":
+        rec["wvariant"] = np.array(variant)
+    if pos_interp != "size":
+        rec["pos_interp"] = np.array(pos_interp)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
     print(name, score.shape, "mean", rec["score_mean"], "min/max", score.min(), score.max())
 
@@ -93,6 +128,14 @@ def run_case(core, name, B, N, H, W, seed_w=1, seed_x=0, need_w=False, head_id=0
 def main():
     torch.set_num_threads(os.cpu_count())
     core = boot_reference()
+    only = sys.argv[1:]
+    global run_case
+    _run = run_case
+
+    def run_case(core, name, *a, **k):  # `python make_golden.py g8 g9`: regenerate only the named cases
+        if not only or any(name.startswith(o) for o in only):
+            _run(core, name, *a, **k)
+
     # G1: tiny square grid (5x5 patches), DINOv2 pos-emb goes through the bicubic path
     run_case(core, "g1_tiny_70x70_n2", 1, 2, 70, 70, save_feats=True)
     # G2: non-square (6x8 patches, ragged 84x117 -> 84x112 map), batch 2, attention-weight export
@@ -111,6 +154,17 @@ def main():
     run_case(core, "g6_pe_shortcut_70x70", 1, 1, 70, 70, pe=(5, 5))
     # G7: 1 reference, more tokens than one attention tile (12x11 patches = 132 tokens)
     run_case(core, "g7_168x154_n1", 1, 1, 168, 154)
+    # G8: BASELINE cfg 4 at its real size: 1 query x 64 reference views at 518x518 (87 616 reference tokens)
+    run_case(core, "g8_518_n64", 1, 64, 518, 518, seed_x=3, subsample=(5, 9))
+    # G9: BASELINE cfg 5's path: 1036x1036 (74x74 patches, T = 5477; DINOv2 pos-emb bicubic 37^2 -> 74^2), 4 refs
+    run_case(core, "g9_1036_n4", 1, 4, 1036, 1036, seed_x=4, subsample=(6, 11))
+    # G10: outlier-channel / wide-LayerScale weights (crossscore_b200.synthetic variant "outlier")
+    run_case(core, "g10_outlier_168x154_n2", 1, 2, 168, 154, seed_w=3, seed_x=5, variant="outlier", save_feats=True)
+    run_case(core, "g10_outlier_518_n5", 1, 5, 518, 518, seed_w=3, seed_x=6, variant="outlier", subsample=(2, 9))
+    # G11: the pinned stack's position-embedding resample (transformers 4.33.3: scale_factor form) on the default
+    # predict geometry (short side 518, no crop -> non-square 37x49 grid) and on a small ragged grid
+    run_case(core, "g11_legacy_pos_84x117_n3", 2, 3, 84, 117, pos_interp="scale_factor", save_feats=True)
+    run_case(core, "g11_legacy_pos_518x690_n2", 1, 2, 518, 690, seed_x=7, pos_interp="scale_factor", subsample=(4, 9))
 
 
 if __name__ == "__main__":

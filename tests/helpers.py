@@ -23,9 +23,16 @@ def golden_problem(rec):
     """Rebuild the seeded weights / inputs a golden case was generated with."""
     over = rec["cfg_over"]
     do_sa = over.get("model__decoder_do_self_attn", True)
-    sd = make_state_dict(int(rec["seed_w"]), pe_h=int(rec["pe_h"]), pe_w=int(rec["pe_w"]), do_self_attn=do_sa)
+    variant = str(rec["wvariant"]) if "wvariant" in rec else "benign"
+    sd = make_state_dict(int(rec["seed_w"]), pe_h=int(rec["pe_h"]), pe_w=int(rec["pe_w"]), do_self_attn=do_sa,
+                         variant=variant)
     q, r = make_inputs(int(rec["B"]), int(rec["N"]), int(rec["H"]), int(rec["W"]), int(rec["seed_x"]))
     return sd, q, r
+
+
+def golden_pos_interp(rec):
+    """Goldens without the field were generated with this container's transformers 5.5.0 (size= form)."""
+    return str(rec["pos_interp"]) if "pos_interp" in rec else "size"
 
 
 def oracle_kwargs(over):

@@ -235,32 +235,102 @@ def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale):
     assert (lse - lse_ref).abs().max() < 0.02
 
 
-@pytest.mark.parametrize("B,H,Lq,Lk,d,nsplit,shared,qscale,folded", [
-    (1, 1, 128, 128, 64, 1, False, 1.0, True),     # single tile
-    (1, 2, 128, 256, 64, 1, False, 1.0, True),     # two kv blocks
-    (1, 2, 128, 192, 64, 1, False, 1.0, True),     # odd number of kv blocks (register buffers swap roles)
-    (2, 6, 1370, 1370, 64, 1, False, 1.0, True),   # DINOv2 shape, ragged tails (odd tail: 1370 = 21*64 + 26)
-    (2, 6, 1370, 1370, 64, 1, False, 1.0, False),  # general scale (HFMA2 with a rounded scale)
-    (1, 8, 128, 128, 48, 1, False, 1.0, True),     # d=48 single tile
-    (2, 8, 1369, 1369, 48, 1, False, 2.0, True),   # decoder self-attention, odd tail (1369 = 21*64 + 25)
-    (1, 8, 300, 6845, 48, 1, False, 3.0, True),    # cross-attention, long kv, peaky softmax (rescale path)
-    (1, 8, 300, 6845, 48, 4, False, 1.0, True),    # split-KV + merge
-    (3, 8, 200, 700, 48, 1, True, 1.0, True),      # shared reference K/V
-    (1, 6, 257, 5000, 64, 1, False, 6.0, True),    # very peaky rows: P overflow detector / fp16 range
+@pytest.mark.parametrize("B,H,Lq,Lk,d,nsplit,shared,qscale", [
+    (1, 2, 128, 256, 64, 1, False, 1.0),
+    (2, 6, 1370, 1370, 64, 1, False, 1.0),
+    (1, 8, 300, 6845, 48, 1, False, 3.0),
+    (1, 8, 300, 6845, 48, 4, False, 1.0),
+    (3, 8, 200, 700, 48, 1, True, 1.0),
 ])
-def test_flash_attn_f16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale, folded):
-    """fp16 operands, fp16 logit accumulators, packed-half softmax.  `folded`: the caller pre-multiplied q by
-    scale*log2(e) (here: plain scale = ln 2 on the given q, i.e. logits are log2-domain), so scale_log2 == 1."""
-    scale = math.log(2.0) if folded else None
-    o, ref, lse, lse_ref = run_attn(DT_F16, B, H, Lq, Lk, d, 64, nsplit, shared, qscale=qscale * (0.35 if folded else 1.0),
-                                    scale=scale)
+def test_flash_attn_bf16_tc_online_pass(B, H, Lq, Lk, d, nsplit, shared, qscale):
+    """xs_attn_set_optimistic(0): every tile goes through the second (online softmax, per-block row max, O rescale)
+    pass -- the path that otherwise only runs for tiles whose row sums left the safe range."""
+    _lib.load().xs_attn_set_optimistic(0)
+    try:
+        o, ref, lse, lse_ref = run_attn(DT_BF16, B, H, Lq, Lk, d, 64, nsplit, shared, qscale=qscale)
+    finally:
+        _lib.load().xs_attn_set_optimistic(1)
     assert torch.isfinite(o).all()
     err = (o - ref).abs()
-    # fp16 logits: an absolute error of |s| * 2^-11 in the exponent; the very peaky case has |s| up to ~60
-    tol = 0.06 if qscale >= 6.0 else 0.03
-    assert err.max() < tol, f"max err {err.max().item()}"
-    assert err.mean() < 3e-3
-    assert (lse - lse_ref).abs().max() < (0.05 if qscale >= 6.0 else 0.02)
+    assert err.max() < 0.03 and err.mean() < 3e-3
+    assert (lse - lse_ref).abs().max() < 0.02
+
+
+def _attn_case(q, k, v, scale, d, nsplit=1):
+    """q (B,Lq,H*64), k/v (B,Lk,H*64) bf16 -> (o, ref, lse, lse_ref) in float64; the reference uses the rounded inputs."""
+    B, Lq, W = q.shape
+    Lk, H = k.shape[1], W // 64
+    o_f32 = 1 if nsplit > 1 else 0
+    o = torch.full((nsplit, B * Lq, H * d), float("nan"), device=DEV, dtype=torch.float32 if o_f32 else torch.bfloat16)
+    lse = torch.full((nsplit, B, H, Lq), float("nan"), device=DEV)
+    call("xs_flash_attn", P(q), P(k), P(v), P(o), P(lse), B, H, Lq, Lk, d, 64, W, Lq * W, W, Lk * W, 0, nsplit, o_f32,
+         scale, DT_BF16, st())
+    if nsplit > 1:
+        merged = torch.empty(B * Lq, H * d, device=DEV, dtype=torch.bfloat16)
+        lse_m = torch.empty(B, H, Lq, device=DEV)
+        call("xs_lse_merge", P(o), P(lse), P(merged), P(lse_m), nsplit, B, Lq, H, d, 0, 0, DT_BF16, st())
+        o, lse = merged, lse_m
+    else:
+        o, lse = o[0], lse[0]
+    torch.cuda.synchronize()
+    qd = q.double().view(B, Lq, H, 64)[..., :d].transpose(1, 2)
+    kd = k.double().view(B, Lk, H, 64)[..., :d].transpose(1, 2)
+    vd = v.double().view(B, Lk, H, 64)[..., :d].transpose(1, 2)
+    ref, lse_ref = attn_ref(qd, kd, vd, scale)
+    return o.double(), ref.transpose(1, 2).reshape(B * Lq, H * d), lse.double(), lse_ref
+
+
+def _ramp_inputs(B, H, Lq, Lk, d, key_logit, seed=0):
+    """Inputs whose logits are (small noise) + key_logit[j] for every query row: feature 0 of q is 1, feature 0 of
+    k carries the wanted per-key offset (values exactly representable in bf16 when multiples of 0.5 below 256)."""
+    q = rnd(B, Lq, H * 64, seed=seed, scale=0.3, dtype=torch.bfloat16)
+    k = rnd(B, Lk, H * 64, seed=seed + 1, scale=0.3, dtype=torch.bfloat16)
+    v = rnd(B, Lk, H * 64, seed=seed + 2, dtype=torch.bfloat16)
+    q.view(B, Lq, H, 64)[..., 0] = 1.0
+    k.view(B, Lk, H, 64)[..., 0] = key_logit.to(DEV).to(torch.bfloat16)[None, :, None]
+    return q, k, v
+
+
+@pytest.mark.parametrize("d", [64, 48])
+@pytest.mark.parametrize("case", ["rising_small", "rising_large", "late_spike", "early_spike", "all_large",
+                                  "all_very_negative", "falling_large"])
+def test_flash_attn_bf16_tc_adversarial_max(case, d):
+    """The softmax reference point.  The first pass takes 2^logit with no maximum at all; rows whose sums leave
+    [2^-80, 2^100] must be caught and redone with the online softmax: a row maximum that rises in every one of >= 100
+    key blocks, a +30 spike in the last block, logits that are all huge or all hugely negative."""
+    Lq, Lk = 200, 100 * 64 + 1  # 101 blocks, tail of ONE key
+    j = torch.arange(Lk, dtype=torch.float32)
+    blk = torch.div(j, 64, rounding_mode="floor")
+    ramp = {
+        "rising_small": blk * 0.5,              # +0.5 per block: max rises 50 over the row (stays optimistic)
+        "rising_large": blk * 2.0,              # +2 per block: 200 over the row -> 2^(288) overflows -> redo
+        "late_spike": torch.where(j == Lk - 1, 30.0, 0.0),
+        "early_spike": torch.where(j == 0, 150.0, 0.0),
+        "all_large": torch.full((Lk,), 120.0),   # every logit ~ +120: P overflows without a reference
+        "all_very_negative": torch.full((Lk,), -120.0),
+        "falling_large": -blk * 2.0,
+    }[case]
+    q, k, v = _ramp_inputs(1, 2, Lq, Lk, d, ramp)
+    o, ref, lse, lse_ref = _attn_case(q, k, v, 1.0, d)
+    assert torch.isfinite(o).all(), case
+    err = (o - ref).abs()
+    assert err.max() < 0.03 and err.mean() < 3e-3, f"{case}: {err.max().item()} {err.mean().item()}"
+    assert (lse - lse_ref).abs().max() < 0.05, case
+
+
+def test_flash_attn_bf16_tc_long_kv_rows_mixed():
+    """Lk = 87 616 (cfg 4 / cfg 5 key count), split and unsplit; half of the query rows see a rising maximum that
+    overflows the optimistic pass, the other half stay benign, so redone and first-pass tiles mix in one launch."""
+    Lq, Lk, d, H = 256, 87616, 48, 8
+    j = torch.arange(Lk, dtype=torch.float32)
+    q, k, v = _ramp_inputs(1, H, Lq, Lk, d, j * (300.0 / Lk))
+    q.view(1, Lq, H, 64)[:, :128, :, 0] = 0.0  # first query tile: no ramp
+    for nsplit in (1, 8):
+        o, ref, lse, lse_ref = _attn_case(q, k, v, 1.0 / math.sqrt(d), d, nsplit=nsplit)
+        assert torch.isfinite(o).all()
+        err = (o - ref).abs()
+        assert err.max() < 0.03 and err.mean() < 3e-3, f"nsplit {nsplit}: {err.max().item()}"
+        assert (lse - lse_ref).abs().max() < 0.05
 
 
 def test_gemm_f16_out():

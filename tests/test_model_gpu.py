@@ -10,7 +10,7 @@ import torch
 
 from crossscore_b200 import CrossScoreNet, default_cfg
 from crossscore_b200.synthetic import make_inputs, make_state_dict
-from helpers import GOLDEN_CASES, compare_to_golden, golden_problem, load_golden, oracle_kwargs
+from helpers import GOLDEN_CASES, compare_to_golden, golden_pos_interp, golden_problem, load_golden, oracle_kwargs
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -21,7 +21,9 @@ TOL = {"fp32": (1e-4, 2e-5), "bf16": (1e-2, 1e-3)}
 def build_net(rec, precision):
     cfg = default_cfg(**rec["cfg_over"])
     cfg.model.pos_enc.multi_view.h, cfg.model.pos_enc.multi_view.w = int(rec["pe_h"]), int(rec["pe_w"])
-    net = CrossScoreNet(cfg, precision=precision)
+    # goldens without a "pos_interp" field were generated with this container's transformers 5.5.0 (size= form)
+    pos_interp = golden_pos_interp(rec)
+    net = CrossScoreNet(cfg, precision=precision, dinov2_pos_interp=pos_interp)
     sd, q, r = golden_problem(rec)
     net.load_state_dict(sd, strict=True)
     return net.to(DEV).eval(), q.to(DEV), r.to(DEV)
@@ -113,12 +115,9 @@ def test_errors():
         net(q.to(DEV), r.to(DEV), True, 8, False)
 
 
-@pytest.mark.parametrize("fuse", ["0", "1"])
-@pytest.mark.parametrize("chunk", ["1", "3", "5"])
-def test_chunked_backbone_matches_unchunked(chunk, fuse, monkeypatch):
-    """The backbone may run a few images at a time (L2-resident intermediates) and with the residual add in the
-    GEMM epilogue or in the LayerNorm kernel: every plan gives the same score map (queries and references
-    straddle chunk boundaries: 2 queries + 2x3 references = 8 images)."""
+def test_residual_plan_variants_agree(monkeypatch):
+    """bf16 mode: residual add in the GEMM epilogue (default) or in the LayerNorm kernel (XS_FUSE_RESIDUAL=0, the
+    pre-fusion plan kept for A/B measurements) give the same score map up to the bf16 rounding of the delta."""
     sd = make_state_dict(3)
     q, r = make_inputs(2, 3, 112, 84, seed=5)
     q, r = q.to(DEV), r.to(DEV)
@@ -131,30 +130,37 @@ def test_chunked_backbone_matches_unchunked(chunk, fuse, monkeypatch):
         torch.cuda.synchronize()
         return out
 
-    monkeypatch.setenv("XS_CHUNK_IMAGES", "0")
     monkeypatch.setenv("XS_FUSE_RESIDUAL", "0")
     base = run()
-    monkeypatch.setenv("XS_CHUNK_IMAGES", chunk)
-    monkeypatch.setenv("XS_FUSE_RESIDUAL", fuse)
+    monkeypatch.setenv("XS_FUSE_RESIDUAL", "1")
     got = run()
-    tol = 1e-6 if fuse == "0" else 5e-3  # the fused plan does not round the residual delta to bf16
-    assert (got - base).abs().max().item() <= tol
+    assert (got - base).abs().max().item() <= 5e-3
 
 
-def test_fp16_logit_attention_plan_parity(monkeypatch):
-    """XS_ATTN_F16=1: fp16 q/k/v, fp16 logit accumulators, scale folded into the query projections -- same
-    tolerances against the reference's golden vectors as the default plan."""
-    monkeypatch.setenv("XS_ATTN_F16", "1")
-    for case in ("g2_nonsquare_84x117_n3_attn", "g7_168x154_n1"):
-        rec = load_golden(case)
-        net, q, r = build_net(rec, "bf16")
-        out = net(q, r, bool(rec["need_w"]), int(rec["head_id"]), False)
-        torch.cuda.synchronize()
-        mx, mean = compare_to_golden(out["score_map_ref_cross"], rec)
-        assert mx <= 1e-2 and mean <= 1e-3, f"{case}: max {mx:.3e} mean {mean:.3e}"
-        if rec["need_w"]:
-            d = np.abs(out["attn_weights_map_ref_cross"].float().cpu().numpy() - rec["attn"])
-            assert d.max() <= 2e-3
+def test_in_place_weight_edit_is_seen():
+    """packed device weights must follow in-place edits of the source parameters."""
+    net = CrossScoreNet(default_cfg(), precision="bf16")
+    net.load_state_dict(make_state_dict(3))
+    net = net.to(DEV).eval()
+    q, r = make_inputs(1, 2, 70, 70, seed=5)
+    q, r = q.to(DEV), r.to(DEV)
+    a = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    net.ref_cross.head._modules["2"].bias.data.add_(0.5)
+    b = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    assert (a - b).abs().max().item() > 1e-2
+    net.ref_cross.head._modules["2"].bias.data.sub_(0.5)
+    c = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    assert torch.equal(a, c)
+
+
+def test_get_featmaps_does_not_touch_forward_tables():
+    """get_featmaps passes its zero PE table as an argument (it used to swap it into the engine's shared cache)."""
+    rec = load_golden("g2_nonsquare_84x117_n3_attn")
+    net, q, r = build_net(rec, "bf16")
+    a = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    net.get_featmaps(q, r)
+    b = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])

@@ -5,9 +5,9 @@ import pytest
 import torch
 
 from oracle import crossscore_oracle as O
-from helpers import GOLDEN_CASES, compare_to_golden, golden_problem, load_golden, oracle_kwargs
+from helpers import GOLDEN_CASES, compare_to_golden, golden_pos_interp, golden_problem, load_golden, oracle_kwargs
 
-SMALL = [c for c in GOLDEN_CASES if "518" not in c]
+SMALL = [c for c in GOLDEN_CASES if "518" not in c and "1036" not in c]
 
 
 @pytest.mark.parametrize("case", SMALL)
@@ -15,7 +15,7 @@ def test_oracle_matches_reference_fp64(case):
     rec = load_golden(case)
     sd, q, r = golden_problem(rec)
     out = O.crossscore_forward(sd, q, r, need_attn_weights=bool(rec["need_w"]), head_id=int(rec["head_id"]),
-                               dt=torch.float64, **oracle_kwargs(rec["cfg_over"]))
+                               dt=torch.float64, pos_interp=golden_pos_interp(rec), **oracle_kwargs(rec["cfg_over"]))
     mx, mean = compare_to_golden(out["score_map_ref_cross"], rec)
     # the reference ran in fp32; fp64 restatement agrees to fp32 round-off
     assert mx < 2e-5 and mean < 2e-6, (mx, mean)
@@ -26,9 +26,11 @@ def test_oracle_matches_reference_fp64(case):
         assert np.abs(a - rec["attn"]).max() < 1e-6
     if "feat_query" in rec:
         assert np.abs(out["_featmap_query"].numpy() - 0).max() > 0  # sanity
-        fq, fr = O.get_featmaps(sd, q, r, torch.float64)
-        assert np.abs(fq.float().numpy() - rec["feat_query"]).max() < 5e-5
-        assert np.abs(fr.float().numpy() - rec["feat_ref"]).max() < 5e-5
+        fq, fr = O.get_featmaps(sd, q, r, torch.float64, golden_pos_interp(rec))
+        # fp32 reference noise scales with the feature magnitude (outlier-channel weights: |f| up to ~100)
+        ftol = 5e-5 * max(1.0, float(np.abs(rec["feat_query"]).max()) / 10.0)
+        assert np.abs(fq.float().numpy() - rec["feat_query"]).max() < ftol
+        assert np.abs(fr.float().numpy() - rec["feat_ref"]).max() < ftol
 
 
 def test_oracle_matches_reference_518_fp32():
@@ -46,7 +48,7 @@ def test_fast_cpu_variant_matches_reference():
     sd, q, r = golden_problem(rec)
     O.FAST = True
     try:
-        out = O.crossscore_forward(sd, q, r, dt=torch.float32)
+        out = O.crossscore_forward(sd, q, r, dt=torch.float32, pos_interp=golden_pos_interp(rec))
     finally:
         O.FAST = False
     mx, mean = compare_to_golden(out["score_map_ref_cross"], rec)
@@ -62,6 +64,14 @@ def test_resamplers_match_torch_interpolate():
     for oh, ow in [(5, 5), (6, 8), (37, 49), (74, 74), (12, 11)]:
         want = F.interpolate(t.permute(2, 0, 1)[None], size=(oh, ow), mode="bicubic", align_corners=False)[0].permute(1, 2, 0)
         assert (O.bicubic_resize_ac_false(t, oh, ow) - want).abs().max() < 1e-12
+    # transformers 4.33.3 (the reference's pinned version): scale_factor=((oh + 0.1) / 37, (ow + 0.1) / 37)
+    for oh, ow in [(5, 5), (6, 8), (37, 49), (74, 74), (12, 11), (37, 65)]:
+        sf = ((oh + 0.1) / 37, (ow + 0.1) / 37)
+        want = F.interpolate(t.permute(2, 0, 1)[None], scale_factor=sf, mode="bicubic", align_corners=False)[0].permute(1, 2, 0)
+        assert want.shape[:2] == (oh, ow)
+        got = O.bicubic_resize_ac_false(t, oh, ow, 1.0 / sf[0], 1.0 / sf[1])
+        assert (got - want).abs().max() < 1e-12
+        assert (got - O.bicubic_resize_ac_false(t, oh, ow)).abs().max() > 1e-3  # and it is NOT the size= form
     t = torch.randn(40, 40, 16, generator=g, dtype=torch.float64)
     for oh, ow in [(5, 5), (6, 8), (37, 37), (37, 49), (74, 74)]:
         want = F.interpolate(t.permute(2, 0, 1)[None], scale_factor=((oh + 1e-4) / 40, (ow + 1e-4) / 40),
