@@ -4,8 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision bf16|fp32]
 
 One "step" = one forward of B=32 queries x 5 reference views at 518x518 (BASELINE.json configs[1]) per GPU.
-N>1 is launched by torchrun (one rank per GPU): queries shard across ranks with no data-path collective
-(weak scaling); NCCL is used only for the barrier and the max-over-ranks time.
+N>1 is launched by torchrun (one rank per GPU): the headline `value` shards queries across ranks with no data-path
+collective (weak scaling).  The same line carries, for N>1, the two schedules that DO exchange
+data over NCCL / NVLink -- `cfg3` (1024-frame scene, shared reference K/V cache broadcast once) and `cfg4` (1 query x
+64 references, split-KV cross-attention merged per decoder layer) -- each with a parity field against the
+single-GPU path; and for N=1 `cfg5` (1036x1036 x 16 refs), `fp32_mode` (the parity mode's speed) and `torch_gpu`
+(the oracle's torch ops on the same B200 under bf16 autocast: the same-box library comparator).
 Prints ONE JSON line (rank 0).  --impl reference times the CPU oracle port of the reference path on the
 host cores (the reference is pure Python/PyTorch and is not present on the GPU box).
 """
@@ -25,14 +29,22 @@ N_REF = 5
 C = 384
 
 
-def flops_per_map(P=1369, N=N_REF):
-    """Algorithmic FLOPs per score map (SURVEY.md section 8d convention)."""
+def flops_per_map(P=1369, N=N_REF, query_only=False):
+    """Algorithmic FLOPs per score map (SURVEY.md section 8d convention).  query_only: the reference views' backbone
+    passes and K/V projections are cached per scene (cfg 3), so a map costs one backbone pass + the decoder."""
     T, M = P + 1, N * P
     f_dino = 2 * P * 588 * C + 12 * (2 * T * C * 3 * C + 4 * T * T * C + 2 * T * C * C + 4 * T * C * 4 * C)
     f_dec = 2 * (2 * P * C * 3 * C + 4 * P * P * C + 2 * P * C * C + 2 * P * C * C + 2 * M * C * 2 * C
                  + 4 * P * M * C + 2 * P * C * C + 4 * P * C * C)
     f_head = 2 * P * C * C + 2 * P * C * 196
+    if query_only:
+        return f_dino + (f_dec - 2 * 2 * M * C * 2 * C) + f_head
     return (1 + N) * f_dino + f_dec + f_head
+
+
+def attn_flops_per_map(P=1369, N=N_REF):
+    T, M = P + 1, N * P
+    return (1 + N) * 12 * 4 * T * T * C + 2 * (4 * P * P * C + 4 * P * M * C)
 
 
 class ClockSampler(threading.Thread):
@@ -135,6 +147,200 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------------
+def _time_ms(fn, iters, warm, sync):
+    """Mean CUDA-event milliseconds of fn() on the current stream (warm untimed calls first)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) / iters
+
+
+def profile_kernels(net, dev, fn, pk):
+    """One instrumented pass of fn(): per-tag launch count, ms, achieved TFLOP/s or GB/s (CUDA events per operator)."""
+    import torch
+    eng = net._engine(dev)
+    eng.prof = []
+    fn()
+    torch.cuda.synchronize()
+    agg = {}
+    for tag, fl, nb, s, e in eng.prof:
+        a = agg.setdefault(tag, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += fl
+        a[2] += nb
+        a[3] += s.elapsed_time(e)
+    eng.prof = None
+    step_ms = sum(a[3] for a in agg.values())
+    kernels = {}
+    for tag, (n, fl, nb, ms) in sorted(agg.items(), key=lambda kv: -kv[1][3]):
+        ent = {"launches": n, "ms": round(ms, 4), "share": round(ms / step_ms, 4)}
+        if fl > 0:
+            ent["tflops"] = round(fl / (ms * 1e-3) / 1e12, 2)
+            ent["frac_of_tensor_peak_sustained"] = round(ent["tflops"] / pk["tensor_sustained"], 4)
+        elif nb > 0:
+            ent["gbs"] = round(nb / (ms * 1e-3) / 1e9, 1)
+            ent["frac_of_hbm_peak"] = round(ent["gbs"] / pk["hbm"], 4)
+        kernels[tag] = ent
+    return agg, kernels, step_ms
+
+
+def extra_single_gpu(net, dev, args, pk):
+    """N = 1 only: BASELINE cfg 5, the fp32 parity mode's speed, and the same-box torch comparator."""
+    import torch
+    from crossscore_b200 import CrossScoreNet, default_cfg
+    from crossscore_b200.synthetic import make_inputs, make_state_dict
+    sync = torch.cuda.synchronize
+    out = {}
+    # ---- cfg 5: 1 query x 16 refs at 1036x1036 (74x74 patches, T = 5477, 87 616 reference tokens), bf16 ----
+    q5, r5 = (t.to(dev) for t in make_inputs(1, 16, 1036, 1036, seed=5))
+    f5 = lambda: net(q5, r5, False, 0, False)
+    ms = _time_ms(f5, 5, 2, sync)
+    fpm = flops_per_map(5476, 16)
+    agg, kernels, _ = profile_kernels(net, dev, f5, pk)
+    a = agg["attn_dino"]
+    ach = a[1] / (a[3] * 1e-3) / 1e12
+    afl = sum(v[1] for t, v in agg.items() if t.startswith("attn_"))
+    ams = sum(v[3] for t, v in agg.items() if t.startswith("attn_"))
+    out["cfg5"] = {"workload": "cfg5: 1 query x 16 refs, 1036x1036 (P = 5476), bf16, device-resident", "ms_per_map": ms,
+                   "maps_per_s": 1e3 / ms, "tflops": fpm / (ms * 1e-3) / 1e12,
+                   "frac_of_tensor_peak_sustained": fpm / (ms * 1e-3) / 1e12 / pk["tensor_sustained"],
+                   "attention_share_of_flops": attn_flops_per_map(5476, 16) / fpm,
+                   "attention_tflops": afl / (ams * 1e-3) / 1e12,
+                   "roofline": {"bound": "tensor", "kernel": "attn_dino", "achieved": ach, "peak": pk["tensor_sustained"],
+                                "unit": "TFLOP/s", "frac": ach / pk["tensor_sustained"],
+                                "algorithmic_flops_per_launch": a[1] / a[0], "avg_launch_ms": a[3] / a[0]},
+                   "kernels": {k: kernels[k] for k in list(kernels)[:6]}}
+    del q5, r5
+    # ---- fp32 parity mode on the headline shape (SIMT fp32 kernels; max-abs <= 1e-4 vs the reference) ----
+    B32 = 4
+    net32 = CrossScoreNet(default_cfg(), precision="fp32")
+    net32.load_state_dict(make_state_dict(1))
+    net32 = net32.to(dev).eval()
+    q, r = (t.to(dev) for t in make_inputs(B32, N_REF, H, W, seed=100))
+    ms = _time_ms(lambda: net32(q, r, False, 0, False), 2, 1, sync)
+    got32 = net32(q, r, False, 0, False)["score_map_ref_cross"]
+    got16 = net(q, r, False, 0, False)["score_map_ref_cross"]
+    d = (got32 - got16).abs()
+    out["fp32_mode"] = {"workload": f"cfg2 shape, batch {B32} x {N_REF} refs, {H}x{W}, precision=fp32", "ms_per_step": ms,
+                        "maps_per_s": B32 * 1e3 / ms, "tflops": B32 * flops_per_map() / (ms * 1e-3) / 1e12,
+                        "bf16_vs_fp32_max_abs": float(d.max()), "bf16_vs_fp32_mean_abs": float(d.mean())}
+    del net32
+    # ---- same-box library comparator: the oracle's torch ops on this B200, bf16 autocast, eager ----
+    try:
+        from oracle import crossscore_oracle as O
+        sd_dev = {k: v.to(dev) for k, v in make_state_dict(1).items()}
+        Bt = args.batch
+        qt, rt = (t.to(dev) for t in make_inputs(Bt, N_REF, H, W, seed=100))
+        O.FAST = True
+
+        def torch_fwd():
+            with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return O.crossscore_forward(sd_dev, qt, rt, dt=torch.float32)["score_map_ref_cross"]
+        ms = _time_ms(torch_fwd, 3, 2, sync)
+        ours = net(qt, rt, False, 0, False)["score_map_ref_cross"]
+        dd = (torch_fwd().float() - ours).abs()
+        out["torch_gpu"] = {"what": "oracle restatement run by torch on this GPU: F.linear / F.scaled_dot_product_attention / "
+                                    "F.layer_norm / F.gelu under torch.autocast(bfloat16), eager, device-resident inputs",
+                            "workload": f"cfg2: batch {Bt} x {N_REF} refs, {H}x{W}", "ms_per_step": ms,
+                            "value": Bt * 1e3 / ms, "unit": "maps/s",
+                            "max_abs_vs_ours": float(dd.max()), "mean_abs_vs_ours": float(dd.mean())}
+        O.FAST = False
+    except Exception as e:  # the comparator must never take the bench line down
+        out["torch_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_multi_gpu(net, dev, world, rank, pk, tmax, barrier):
+    """N > 1: the two schedules of north-star item (4) that exchange data between GPUs, with parity fields.
+    cfg3: a scene of 1024 query frames sharing ONE set of 5 references (reference views sharded over the ranks, K/V of
+    both decoder layers exchanged once over NCCL, then queries shard).  cfg4: 1 query x 64 references, reference
+    tokens sharded (split-KV cross-attention; partial O + LSE merged per decoder layer over NVLink peer memory or
+    one NCCL all-gather)."""
+    import torch
+    from crossscore_b200.scene import SceneScorer, SplitKVScorer, shard_range
+    from crossscore_b200.synthetic import make_inputs
+    eng = net._engine(dev)
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.inference_mode():
+        # ---------------- cfg 3 ----------------
+        Q, Bq = 1024, 32
+        _, refs = make_inputs(1, N_REF, H, W, seed=7)
+        refs = refs[0].to(dev)
+        lo, hi = shard_range(Q, world, rank)
+        q_mine, _ = make_inputs(Bq, 1, H, W, seed=100 + rank)  # one resident batch reused for the rank's share
+        q_mine = q_mine.to(dev)
+        sc = SceneScorer(eng, dev)
+        sc.build_reference_cache(refs)
+        sc.score(q_mine)
+        barrier()
+        e0.record()
+        sc.build_reference_cache(refs)
+        e1.record()
+        barrier()
+        ms_cache = tmax(e0.elapsed_time(e1))
+        n_batches = (hi - lo + Bq - 1) // Bq
+        barrier()
+        e0.record()
+        for _ in range(n_batches):
+            s = sc.score(q_mine)
+        e1.record()
+        barrier()
+        ms_score = tmax(e0.elapsed_time(e1))
+        # parity: the same 4 queries through the plain forward (every query carries its own copy of the references)
+        want = net(q_mine[:4], refs[None].expand(4, -1, -1, -1, -1).contiguous(), False, 0, False)["score_map_ref_cross"]
+        d3 = tmax(float((sc.score(q_mine[:4]) - want).abs().max()))
+        f3 = flops_per_map(query_only=True)
+        out["cfg3"] = {"workload": f"cfg3: {Q} query frames sharing one set of {N_REF} refs, {H}x{W}, queries sharded over "
+                                   f"{world} GPUs in batches of {Bq}", "cache_build_ms": ms_cache,
+                       "cache_bytes_received_per_rank": sc.cache_bytes_received, "score_ms": ms_score,
+                       "maps_per_s_excl_cache": Q / (ms_score * 1e-3),
+                       "maps_per_s_incl_cache": Q / ((ms_score + ms_cache) * 1e-3),
+                       "gflop_per_map": f3 / 1e9, "tflops_excl_cache": Q * f3 / (ms_score * 1e-3) / 1e12,
+                       "frac_of_tensor_peak_sustained": Q * f3 / (ms_score * 1e-3) / 1e12 / world / pk["tensor_sustained"],
+                       "parity": {"max_abs_vs_plain_forward": d3, "max_over": "ranks, 4 queries each"}}
+        # ---------------- cfg 4 ----------------
+        q1, r64 = (t.to(dev) for t in make_inputs(1, 64, H, W, seed=9))
+        c4 = {"workload": f"cfg4: 1 query x 64 refs, {H}x{W}; reference views sharded over {world} GPUs (split-KV)"}
+        got = None
+        for mode in ("p2p", "nccl"):
+            sk = SplitKVScorer(eng, dev, exchange=mode)
+            g = sk.forward(q1, r64).clone()
+            got = g if got is None else got
+            sk.forward(q1, r64)
+            barrier()
+            e0.record()
+            for _ in range(10):
+                sk.forward(q1, r64)
+            e1.record()
+            barrier()
+            c4[f"ms_per_query_{sk.exchange}"] = tmax(e0.elapsed_time(e1)) / 10
+            c4[f"exchange_bytes_per_query_{sk.exchange}"] = sk.allgather_bytes or sk.peer_bytes_pulled
+        full = net(q1, r64, False, 0, False)["score_map_ref_cross"]
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            net(q1, r64, False, 0, False)
+        e1.record()
+        torch.cuda.synchronize()
+        one = e0.elapsed_time(e1) / 3
+        c4["ms_per_query_one_gpu"] = tmax(one)
+        best = min(v for k, v in c4.items() if k.startswith("ms_per_query_") and k != "ms_per_query_one_gpu")
+        c4["speedup_vs_one_gpu"] = c4["ms_per_query_one_gpu"] / best
+        c4["parity"] = {"max_abs_vs_one_gpu": tmax(float((full - got).abs().max())), "max_over": "ranks"}
+        out["cfg4"] = c4
+    return out
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -248,30 +454,8 @@ def run_ours(args):
     latency = {"workload": "cfg1: 1 query x 5 refs, 518x518, device-resident inputs", **lat}
 
     # ---- per-kernel roofline (instrumented pass, CUDA events on the launching stream) --------------------
-    eng = net._engine(dev)
-    eng.prof = []
-    net(q_dev, r_dev, False, 0, False)
-    torch.cuda.synchronize()
-    agg = {}
-    for tag, fl, nb, s, e in eng.prof:
-        a = agg.setdefault(tag, [0, 0.0, 0.0, 0.0])
-        a[0] += 1
-        a[1] += fl
-        a[2] += nb
-        a[3] += s.elapsed_time(e)
-    eng.prof = None
     pk = peaks()
-    step_ms = sum(a[3] for a in agg.values())
-    kernels = {}
-    for tag, (n, fl, nb, ms) in sorted(agg.items(), key=lambda kv: -kv[1][3]):
-        ent = {"launches": n, "ms": round(ms, 4), "share": round(ms / step_ms, 4)}
-        if fl > 0:
-            ent["tflops"] = round(fl / (ms * 1e-3) / 1e12, 2)
-            ent["frac_of_tensor_peak_sustained"] = round(ent["tflops"] / pk["tensor_sustained"], 4)
-        elif nb > 0:
-            ent["gbs"] = round(nb / (ms * 1e-3) / 1e9, 1)
-            ent["frac_of_hbm_peak"] = round(ent["gbs"] / pk["hbm"], 4)
-        kernels[tag] = ent
+    agg, kernels, step_ms = profile_kernels(net, dev, lambda: net(q_dev, r_dev, False, 0, False), pk)
     top = next(iter(kernels))
     tent = agg[top]
     if tent[1] > 0:
@@ -287,6 +471,14 @@ def run_ours(args):
     attn_fl = sum(a[1] for t, a in agg.items() if t.startswith("attn_") and a[1] > 0)
     attn_ms = sum(a[3] for t, a in agg.items() if t.startswith("attn_") and a[1] > 0)
     attn_tf = attn_fl / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0
+
+    # ---- the other BASELINE configs (kept out of the headline numbers above) ----------------------------------
+    extra = {}
+    if not args.no_extra:
+        if world > 1:
+            extra = extra_multi_gpu(net, dev, world, rank, pk, max_over_ranks, barrier)
+        else:
+            extra = extra_single_gpu(net, dev, args, pk)
 
     if rank != 0:
         if world > 1:
@@ -323,6 +515,8 @@ def run_ours(args):
         "attention_tflops": attn_tf, "attention_frac_of_bf16_peak_sustained": attn_tf / pk["tensor_sustained"],
         "attention_frac_of_bf16_peak_burst": attn_tf / pk["tensor_burst"],
         "kernels": kernels,
+        "kernel_time_share_of_step": step_ms / (ms_total / K),
+        **extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -338,6 +532,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3/cfg4 (N>1) and cfg5/fp32/torch (N=1) blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -11,10 +11,10 @@
 //               warps per SM (four per scheduler) hide each other's TMEM / mbarrier latencies; round 1 ran eight, one
 //               thread per row, and was latency-bound at 32 % tensor-pipe activity.
 //   warp 8      TMA producer: Q tile per tile, then K_j / V_j tiles [64 keys x 64] into a 5-stage ring
-//   warp 9      TMEM allocator + MMA issuer:  S_b = Q K_j^T  (SS, K-major operands, 128B swizzle, N = 64)
-//                                             O  += P_j V_j  (TS: P read from TMEM, V MN-major from smem)
-//   warps 10,11 idle (they only lend registers: setmaxnreg moves 8*96 + 4*40 <= 12*80)
-// S is TRIPLE-BUFFERED in TMEM (S_0..S_2): QK_{j+3} is issued right behind PV_j.
+//   warp 9      TMEM allocator + PV issuer:  O += P_j V_j  (TS: P read from TMEM, V MN-major from smem)
+//   warp 10     QK issuer:  S_b = Q K_j^T  (SS, K-major operands, 128B swizzle, N = 64), up to 3 blocks ahead
+//   warp 11     idle (it only lends registers: setmaxnreg moves 8*96 + 4*40 <= 12*80)
+// S is TRIPLE-BUFFERED in TMEM (S_0..S_2): QK_{j+3} is issued as soon as PV_j has completed (s_free).
 // TMEM (256 columns per CTA): S_b [64b, 64b+64), b = 0..2 (P_b overwrites the upper 32 columns of S_b), O [192, 192+DV).
 //
 // Softmax arithmetic.  Pass 1 ("optimistic") uses NO running maximum: P = 2^(S * scale * log2 e) directly, row sums in
@@ -55,6 +55,36 @@ constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK
 #ifndef ATT_DBG
 #define ATT_DBG 0
 #endif
+// ATT_PROF (development builds only): per-phase clock64 totals of each role (lane 0), printed by the launcher.
+#ifndef ATT_PROF
+#define ATT_PROF 0
+#endif
+struct PhaseClock {
+#if ATT_PROF
+  long long t;
+  unsigned long long acc[8];
+  __device__ __forceinline__ void start() {
+    t = clock64();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0;
+  }
+  __device__ __forceinline__ void lap(int i) {
+    const long long n = clock64();
+    acc[i] += static_cast<unsigned long long>(n - t);
+    t = n;
+  }
+  __device__ __forceinline__ void flush(unsigned long long* out, int base, int lane) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(out + base + i, acc[i]);
+    }
+  }
+#else
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void lap(int) {}
+  __device__ __forceinline__ void flush(unsigned long long*, int, int) {}
+#endif
+};
 constexpr int ATT_MAX_TILES_PER_CTA = 1024;             // redo bitmap capacity
 constexpr float ATT_L_MIN = 8.2718061e-25f;             // 2^-80
 constexpr float ATT_L_MAX = 1.2676506e30f;              // 2^100
@@ -74,6 +104,7 @@ struct AttnParams {
   float scale_log2;
   int nq_tiles, n_tiles;  // 128-query tiles per (batch, head, split); total tiles
   int all_safe;           // skip the optimistic pass (xs_attn_set_optimistic(0), or more tiles per CTA than the bitmap)
+  unsigned long long* prof;  // ATT_PROF builds only
 };
 
 struct TagNo { static constexpr bool value = false; };
@@ -124,9 +155,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const SmemBar kv_empty = kv_full + ATT_ST;   // [ATT_ST] PV_g complete: slot free (also read by the O rescale)
   const SmemBar s_full = kv_empty + ATT_ST;    // [ATT_NS]
   const SmemBar p_full = s_full + ATT_NS;      // [ATT_NS]
-  const SmemBar o_full = p_full + ATT_NS;      // all PV of the tile complete
+  const SmemBar s_free = p_full + ATT_NS;      // [ATT_NS] PV_g complete: S buffer g % ATT_NS may be overwritten
+  const SmemBar o_full = s_free + ATT_NS;      // all PV of the tile complete
   const SmemBar o_empty = o_full + 1;          // O read out by the softmax warps: next tile's PV_0 may overwrite
-  constexpr int N_BARS = 2 + 2 * ATT_ST + 2 * ATT_NS + 2;
+  constexpr int N_BARS = 2 + 2 * ATT_ST + 3 * ATT_NS + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
   uint32_t* redo = tmem_slot + 2;  // [ATT_MAX_TILES_PER_CTA / 32] bitmap over this CTA's tile sequence
 
@@ -146,6 +178,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int s = 0; s < ATT_NS; ++s) {
       mbar_init(s_full + (s), 1);
       mbar_init(p_full + (s), 8);  // one arrival per softmax warp
+      mbar_init(s_free + (s), 1);
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, 8);
@@ -171,13 +204,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 8) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     uint32_t g = 0, n_done = 0;
+    PhaseClock pc;
+    pc.start();
     for (int pass = 0; pass < 2; ++pass) {
       int idx = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++idx) {
         if (!selected(pass, idx)) continue;
         const TileCoord t = decode_tile(tile, p);
         const int b_kv = p.kv_shared ? 0 : t.b;
+        pc.lap(3);
         mbar_wait(q_empty, (n_done & 1) ^ 1);  // previous tile's QK^T are done with the Q buffer
+        pc.lap(0);
         if (elect_one_sync()) {
           mbar_expect_tx(q_full, ATT_Q_BYTES);
           tma_load_3d(smQ, &tmQ, q_full, t.h * 64, t.q0, t.b);
@@ -186,7 +223,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < t.nkv; ++j, ++g) {
           const uint32_t s = g % ATT_ST;
           const int kv0 = t.kv_begin + j * ATT_BKV;
+          pc.lap(3);
           mbar_wait(kv_empty + (s), ((g / ATT_ST) & 1) ^ 1);
+          pc.lap(1);
           if (elect_one_sync()) {
             if ((ATT_DBG & 1) && g >= ATT_ST) {
               mbar_arrive(kv_full + (s));
@@ -197,52 +236,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
           }
           __syncwarp();
+          pc.lap(2);
         }
         ++n_done;
       }
       if (pass == 0) named_bar_sync(1, ATT_THREADS);
     }
+    pc.flush(p.prof, 16, lane);
   } else if (warp == 9) {
-    // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BKV, 0, 0);
+    // ===================== PV issuer (converged warp, uniform operands, one elected lane issues) =========
+    // O += P_g V_g as soon as the softmax warps have handed P_g over.  Its completion frees the K/V ring slot (TMA
+    // warp), the S buffer P_g lived in (QK issuer) and, for the last block, publishes O (softmax epilogue).
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major ([kv][d], d contiguous)
     const uint32_t tb = warp_uniform(tmem_base);
-    const uint32_t q_lo = umma_desc_lo(smem_u32(smQ), 16);
-    const uint32_t k_lo0 = umma_desc_lo(smem_u32(smK), 16);
     const uint32_t v_lo0 = umma_desc_lo(smem_u32(smV), 1024);
-    auto issue_qk = [&](uint32_t gg, bool last_of_tile) {
-      const uint32_t s = gg % ATT_ST;
-      mbar_wait(kv_full + (s), (gg / ATT_ST) & 1);  // K_gg (and V_gg) have landed
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
-        const uint32_t d_s = tb + (gg % ATT_NS) * 64;
-        if (!(ATT_DBG & 16)) {
-#pragma unroll
-          for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        }
-        tc_commit(s_full + (gg % ATT_NS));
-        if (last_of_tile) tc_commit(q_empty);  // Q buffer may be refilled once these MMAs have read it
-      }
-      __syncwarp();
-    };
-    uint32_t g0 = 0, n_done = 0;
+    PhaseClock pc;
+    pc.start();
+    uint32_t g = 0, n_done = 0;
     for (int pass = 0; pass < 2; ++pass) {
       int idx = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++idx) {
         if (!selected(pass, idx)) continue;
-        const TileCoord t = decode_tile(tile, p);
-        const int nkv = t.nkv;
-        mbar_wait(q_full, n_done & 1);
-        // the S buffers of the first blocks are free: the previous tile's PVs were issued before (the tensor pipe
-        // executes in order) and the softmax warps had read those S blocks before they arrived on p_full
-        for (int jj = 0; jj < ATT_NS && jj < nkv; ++jj) issue_qk(g0 + jj, jj == nkv - 1);
-        for (int j = 0; j < nkv; ++j) {
-          const uint32_t g = g0 + j;
-          const uint32_t s = g % ATT_ST;
-          const uint32_t sb = g % ATT_NS;
-          mbar_wait(p_full + (sb), (g / ATT_NS) & 1);  // softmax has turned S_sb into P_g
+        const int nkv = decode_tile(tile, p).nkv;
+        uint32_t s = g % ATT_ST, sb = g % ATT_NS, ph_s = (g / ATT_NS) & 1;  // running ring / buffer indices
+        for (int j = 0; j < nkv; ++j, ++g) {
+          pc.lap(6);
+          mbar_wait(p_full + (sb), ph_s);  // softmax has turned S_sb into P_g
+          pc.lap(1);
           if (j == 0) mbar_wait(o_empty, (n_done & 1) ^ 1);  // previous tile's O has been read out
+          pc.lap(2);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t v_lo = v_lo0 + s * (ATT_KV_BYTES >> 4);
@@ -255,17 +277,71 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               }
             }
             tc_commit(kv_empty + (s));  // K_g / V_g slot free; also the "PV_g complete" signal for the O rescale
+            tc_commit(s_free + (sb));   // S_sb may be overwritten by QK_{g+ATT_NS}
             if (j == nkv - 1) tc_commit(o_full);
           }
           __syncwarp();
-          if (j + ATT_NS < nkv) issue_qk(g + ATT_NS, j + ATT_NS == nkv - 1);  // overwrites S_sb behind PV_g
+          pc.lap(3);
+          if (++s == ATT_ST) s = 0;
+          if (++sb == ATT_NS) { sb = 0; ph_s ^= 1; }
         }
-        g0 += nkv;
         ++n_done;
       }
       if (pass == 0) named_bar_sync(1, ATT_THREADS);
     }
-  } else if (warp >= 10) {
+    pc.flush(p.prof, 8, lane);
+  } else if (warp == 10) {
+    // ===================== QK issuer: S_sb = Q K_g^T, running up to ATT_NS blocks ahead of the softmax ==========
+    // Two issuing warps instead of one: every mbarrier wait costs 100-200 clk even when the barrier completed long
+    // ago and a tcgen05.mma issue blocks until the (shallow) tensor queue takes it, so a single warp that serialises
+    // [wait P, 4 PV, commits, wait K, 4 QK, commit] needed ~1200 clk per block and paced the whole CTA (phase clocks,
+    // profiles/r2_attn_phase_clocks.txt).
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BKV, 0, 0);
+    const uint32_t tb = warp_uniform(tmem_base);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(smQ), 16);
+    const uint32_t k_lo0 = umma_desc_lo(smem_u32(smK), 16);
+    PhaseClock pc;
+    pc.start();
+    uint32_t g = 0, n_done = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      int idx = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++idx) {
+        if (!selected(pass, idx)) continue;
+        const int nkv = decode_tile(tile, p).nkv;
+        pc.lap(6);
+        mbar_wait(q_full, n_done & 1);
+        pc.lap(0);
+        uint32_t s = g % ATT_ST, ph_k = (g / ATT_ST) & 1, sb = g % ATT_NS, ph_s = (g / ATT_NS) & 1;
+        for (int j = 0; j < nkv; ++j, ++g) {
+          // both polls are issued before either result is used, so their latencies overlap.  S_sb is free once
+          // PV_{g-ATT_NS} has completed (the wait on the barrier's previous phase passes at once for g < ATT_NS)
+          const bool k_ok = mbar_try_wait(kv_full + (s), ph_k);
+          const bool s_ok = mbar_try_wait(s_free + (sb), ph_s ^ 1);
+          if (!k_ok) mbar_wait(kv_full + (s), ph_k);
+          if (!s_ok) mbar_wait(s_free + (sb), ph_s ^ 1);
+          pc.lap(4);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t k_lo = k_lo0 + s * (ATT_KV_BYTES >> 4);
+            const uint32_t d_s = tb + sb * 64;
+            if (!(ATT_DBG & 16)) {
+#pragma unroll
+              for (int k = 0; k < DQK_STEPS; ++k) umma_ss_lh<false>(d_s, q_lo + 2 * k, k_lo + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+            }
+            tc_commit(s_full + (sb));
+            if (j == nkv - 1) tc_commit(q_empty);  // Q buffer may be refilled once these MMAs have read it
+          }
+          __syncwarp();
+          pc.lap(5);
+          if (++s == ATT_ST) { s = 0; ph_k ^= 1; }
+          if (++sb == ATT_NS) { sb = 0; ph_s ^= 1; }
+        }
+        ++n_done;
+      }
+      if (pass == 0) named_bar_sync(1, ATT_THREADS);
+    }
+    pc.flush(p.prof, 20, lane);
+  } else if (warp == 11) {
     named_bar_sync(1, ATT_THREADS);
   } else {
     // ===================== softmax / epilogue: warp w owns rows [32 (w%4) + 16 (w/4), +16) of the tile ==========
@@ -277,6 +353,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t t_o = tmem_O + lane_off;
     const float sl2 = p.scale_log2;
     uint32_t g0 = 0, n_done = 0;
+    PhaseClock pc;
+    pc.start();
 
     auto tile_fn = [&](const int tile, const int idx, auto safe_tag) {
       constexpr bool SAFE = decltype(safe_tag)::value;
@@ -295,10 +373,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t sb = g % ATT_NS;
         const uint32_t t_s = tmem_base + lane_off + sb * 64;
         uint32_t v[32], pk[16];
+        pc.lap(7);
         mbar_wait(s_full + (sb), (g / ATT_NS) & 1);
+        pc.lap(0);
         tc_fence_after();
         if (!(ATT_DBG & 4) || j == 0) tmem_ld_16x256b_x8(t_s, v);
         tmem_ld_wait32(v);
+        pc.lap(1);
         if constexpr (MASK) {  // last block: columns >= tail_valid are past the sequence end
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -377,18 +458,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         // P_g overwrites the upper half of S_sb (the whole block is in registers by now)
+        pc.lap(2);
         if (!(ATT_DBG & 8)) tmem_st_16x128b_x8(t_s + 32, pk);
         tc_wait_st();
+        pc.lap(3);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full + sb);
+        pc.lap(4);
       };
       for (int j = 0; j + 1 < nkv; ++j) block(j, TagNo{});
       block(nkv - 1, TagYes{});
       g0 += nkv;
 
       // ---- epilogue: read O out of TMEM (frees it for the next tile's PV_0), then O / l and log-sum-exp ----
+      pc.lap(7);
       mbar_wait(o_full, n_done & 1);
+      pc.lap(5);
       tc_fence_after();
       uint32_t o[32];
       if constexpr (DV == 64) {
@@ -453,6 +539,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (rowA < p.Lq) lse[rowA] = (m0A + log2f(la)) * 0.6931471805599453f;
         if (rowB < p.Lq) lse[rowB] = (m0B + log2f(lb)) * 0.6931471805599453f;
       }
+      pc.lap(6);
     };
 
     if (!p.all_safe) {
@@ -465,6 +552,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++idx)
         if (selected(1, idx)) tile_fn(tile, idx, TagYes{});
     }
+    pc.flush(p.prof, 0, lane);
   }
 
   tc_fence_before();
@@ -484,8 +572,29 @@ static int launch_attn(dim3 grid, const CUtensorMap& tmQ, const CUtensorMap& tmK
                        const AttnParams& p, cudaStream_t stream) {
   auto kern = attn_tc_kernel<DQK, DV, SCALE1>;
   XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM_BYTES));
+#if ATT_PROF
+  static unsigned long long* buf = nullptr;
+  if (buf == nullptr) XS_CUDA(cudaMalloc(&buf, 32 * sizeof(unsigned long long)));
+  XS_CUDA(cudaMemsetAsync(buf, 0, 32 * sizeof(unsigned long long), stream));
+  AttnParams pp = p;
+  pp.prof = buf;
+  kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, pp);
+  XS_LAUNCH_CHECK();
+  XS_CUDA(cudaStreamSynchronize(stream));
+  unsigned long long h[32];
+  XS_CUDA(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
+  const double nb = double(p.n_tiles) * ((p.split_len < p.Lk ? p.split_len : p.Lk) + ATT_BKV - 1) / ATT_BKV;  // blocks
+  fprintf(stderr, "attn prof, clk per 64-key block | softmax warp (avg of 8): wait_S %.0f  ld %.0f  math %.0f  st+wait %.0f  "
+                  "arrive %.0f  wait_O %.0f  epilogue %.0f  other %.0f | pv warp: wait_P %.0f  wait_Oempty %.0f  issue_PV %.0f  "
+                  "other %.0f | qk warp: wait_Q %.0f  wait_KV+Sfree %.0f  issue_QK %.0f  other %.0f | tma warp: wait_Qempty %.0f  "
+                  "wait_KVempty %.0f  issue %.0f  other %.0f\n",
+          h[0] / nb / 8, h[1] / nb / 8, h[2] / nb / 8, h[3] / nb / 8, h[4] / nb / 8, h[5] / nb / 8, h[6] / nb / 8, h[7] / nb / 8,
+          h[9] / nb, h[10] / nb, h[11] / nb, h[14] / nb, h[20] / nb, h[24] / nb, h[25] / nb, h[26] / nb, h[16] / nb, h[17] / nb,
+          h[18] / nb, h[19] / nb);
+#else
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   XS_LAUNCH_CHECK();
+#endif
   return 0;
 }
 
@@ -524,6 +633,7 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
   AttnParams p;
   p.o = o;
   p.lse = lse;
+  p.prof = nullptr;
   p.o_is_f32 = o_is_f32;
   p.Lq = Lq;
   p.Lk = Lk;

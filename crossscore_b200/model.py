@@ -95,8 +95,9 @@ class CrossScoreNet(nn.Module):
         return out
 
     def _weights_stamp(self):
-        """Cheap fingerprint of the source parameters: in-place edits (``p.data.copy_()``, ``p.data = ...``) bump
-        ``_version`` or change ``data_ptr``, so the packed copies are rebuilt instead of going stale silently."""
+        """Cheap fingerprint of the source parameters: in-place ops on a parameter (``p.copy_()``, ``p.add_()``) bump
+        its ``_version`` and ``p.data = ...`` changes ``data_ptr``, so the packed copies are rebuilt instead of going
+        stale silently.  In-place ops THROUGH ``p.data`` (``p.data.copy_()``) touch neither: call ``refresh()``."""
         stamp = 0
         for t in list(self.parameters()) + list(self.buffers()):
             stamp = (stamp * 1000003 + t._version * 7919 + t.data_ptr()) & 0xFFFFFFFFFFFF

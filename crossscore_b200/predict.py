@@ -243,6 +243,14 @@ class PredictRunner:
         map_dir = self.out_dir / "batch" / "score_map_ref_cross"
         if self.write_maps:
             map_dir.mkdir(parents=True, exist_ok=True)
+        if shared and len(query_paths) > 0:
+            # The whole scene shares one reference set: encode it once.  build_reference_cache() exchanges K/V slices
+            # with one collective per owning rank, so EVERY rank must get here -- also a rank whose query shard is
+            # empty (more GPUs than frames) -- and before anything that can raise on a single rank.
+            refs = self.be.stack([self._load(p, None, cache=True) for p in refs_all[0]])
+            scorer = self.be.scene_scorer()
+            scorer.build_reference_cache(refs)
+            shared_hw = tuple(refs.shape[-2:])
         for bi, lo in enumerate(range(0, len(mine), self.batch_size)):
             idx = mine[lo:lo + self.batch_size]
             q_u8 = [self.reader(query_paths[i]) for i in idx]
@@ -251,12 +259,8 @@ class PredictRunner:
                 raise ValueError("query images of one batch must have the same size")
             q = self.be.preprocess(np.stack(q_u8, 0), self.resize)
             if shared:
-                if scorer is None:  # the whole scene shares one reference set: encode it once
-                    refs = self.be.stack([self._load(p, raw_shape, cache=True) for p in refs_all[0]])
-                    if tuple(refs.shape[-2:]) != tuple(q.shape[-2:]):
-                        raise ValueError("reference and query images must have the same size after resizing")
-                    scorer = self.be.scene_scorer()
-                    scorer.build_reference_cache(refs)
+                if shared_hw != tuple(q.shape[-2:]):
+                    raise ValueError("reference and query images must have the same size after resizing")
                 score = scorer.score(q).clone()
             else:
                 r = self.be.stack([self.be.stack([self._load(p, raw_shape, cache=True) for p in refs_all[i]]) for i in idx])

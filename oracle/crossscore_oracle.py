@@ -53,6 +53,8 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) ->
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    if FAST:
+        return torch.nn.functional.linear(x, w, b)  # fused bias (addmm), as nn.Linear does
     y = x @ w.transpose(-1, -2)
     return y if b is None else y + b
 
@@ -120,7 +122,7 @@ def bicubic_resize_ac_false(table: torch.Tensor, oh: int, ow: int, step_h=None, 
 
     def axis(o, i, step):
         scale = i / o if step is None else step
-        src = (torch.arange(o, dtype=dt) + 0.5) * scale - 0.5
+        src = (torch.arange(o, dtype=dt, device=table.device) + 0.5) * scale - 0.5
         fl = torch.floor(src)
         t = src - fl
         idx = fl.long()
@@ -129,10 +131,10 @@ def bicubic_resize_ac_false(table: torch.Tensor, oh: int, ow: int, step_h=None, 
 
     ty, wy = axis(oh, ih, step_h)
     tx, wx = axis(ow, iw, step_w)
-    out = torch.zeros(oh, ow, table.shape[2], dtype=dt)
+    out = torch.zeros(oh, ow, table.shape[2], dtype=dt, device=table.device)
     for a in range(4):
         rows = table[ty[a]]  # (oh, iw, C)
-        acc = torch.zeros(oh, ow, table.shape[2], dtype=dt)
+        acc = torch.zeros(oh, ow, table.shape[2], dtype=dt, device=table.device)
         for b in range(4):
             acc = acc + rows[:, tx[b]] * wx[b][None, :, None]
         out = out + acc * wy[a][:, None, None]
@@ -150,9 +152,9 @@ def bilinear_resize_ac_true(table: torch.Tensor, oh: int, ow: int) -> torch.Tens
 
     def axis(o, i):
         if o > 1:
-            src = torch.arange(o, dtype=dt) * ((i - 1) / (o - 1))
+            src = torch.arange(o, dtype=dt, device=table.device) * ((i - 1) / (o - 1))
         else:
-            src = torch.zeros(o, dtype=dt)
+            src = torch.zeros(o, dtype=dt, device=table.device)
         i0 = torch.clamp(torch.floor(src).long(), 0, i - 1)
         i1 = torch.clamp(i0 + 1, 0, i - 1)
         t = src - i0.to(dt)

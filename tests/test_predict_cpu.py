@@ -160,6 +160,15 @@ def test_runner_shared_reference_scene_and_ranks(tmp_path):
         assert be.pre_calls == len(P.shard_indices(7, rank, 2)) + 5
         assert run.write_summary().name == f"scores_r{rank}.csv"
     assert sorted(x[2] for x in rows) == [f"{i:05}.png" for i in range(7)]
+    # more ranks than query frames: a rank with an EMPTY shard still takes part in the one collective
+    # step of the scene -- the reference cache build -- instead of leaving its peers waiting for its K/V slice
+    for rank in range(9):
+        be = FakeBackend()
+        run = P.PredictRunner(be, str(tmp_path / "o9"), "mae", 0, 1, batch_size=4, num_refs=5, deterministic_refs=True,
+                              resize_short_side=-1, colour_mode="gray", rank=rank, world=9, write_maps=False)
+        got = run.run(q, r)
+        assert be.scene_builds == 1, rank
+        assert len(got) == len(P.shard_indices(7, rank, 9))
     # fewer references than requested: empty_image padding -> per-query path (no shared cache)
     be = FakeBackend()
     run = P.PredictRunner(be, str(tmp_path / "o2"), "mae", 0, 1, batch_size=4, num_refs=8, deterministic_refs=True,
