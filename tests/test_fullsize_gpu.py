@@ -98,3 +98,42 @@ def test_cfg5_forward_properties_1036():
     ref = _net(seed=4, precision="fp32")(q, r, False, 0, False)["score_map_ref_cross"]
     d = (out - ref).abs()
     assert d.max().item() <= 1e-2 and d.mean().item() <= 1e-3, (d.max().item(), d.mean().item())
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_cfg4_split_kv_schedule_vs_reference_golden(precision):
+    """BASELINE cfg 4 at its real size (1 query x 64 refs, 518x518) against the golden the UNMODIFIED reference produced
+    (tests/golden/g8_518_n64.npz), through the split-KV schedule of the 8-GPU path run on ONE GPU: the reference
+    views are cut into 8 contiguous shards (crossscore_b200.scene.shard_range), every shard's keys go through
+    Engine.cross_attn_partial into a packed (O_r | LSE_r) part, and Engine.merge_partials combines the 8 parts --
+    exactly what SplitKVScorer does with one rank per shard, minus the transport."""
+    from helpers import compare_to_golden, golden_pos_interp, golden_problem, load_golden
+    from crossscore_b200.scene import shard_range
+    rec = load_golden("g8_518_n64")
+    sd, q, r = golden_problem(rec)
+    net = CrossScoreNet(default_cfg(), precision=precision, dinov2_pos_interp=golden_pos_interp(rec))
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    q, r = q.to(DEV), r.to(DEV)
+    eng = net._engine(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    B, N, P, C, HEADS, PARTS = 1, 64, 37 * 37, 384, 8, 8
+    with torch.inference_mode():
+        xq32, mem = eng.features(q, r, st)
+        kv = eng.project_kv(mem, st)
+        part = B * P * C + B * HEADS * P
+        gathered = torch.empty(PARTS * part, device=DEV, dtype=torch.float32)
+
+        def cross_attn(layer, qc, att, lse_out, st_):
+            for s in range(PARTS):
+                lo, hi = shard_range(N, PARTS, s)
+                eng.cross_attn_partial(layer, qc, kv[lo * P:hi * P], B, P, (hi - lo) * P, gathered[s * part:(s + 1) * part], st_)
+            eng.merge_partials(gathered, PARTS, B, P, att, lse_out, st_)
+
+        score, _ = eng.decode(xq32, None, B, P, N * P, 37, 37, st, cross_attn_fn=cross_attn)
+        plain = net(q, r, False, 0, False)["score_map_ref_cross"]
+    torch.cuda.synchronize()
+    mx, mean = compare_to_golden(score, rec)
+    tmax, tmean = (1e-2, 1e-3) if precision == "bf16" else (1e-4, 2e-5)
+    assert mx <= tmax and mean <= tmean, (mx, mean)
+    assert (score - plain).abs().max().item() <= (5e-3 if precision == "bf16" else 1e-5)

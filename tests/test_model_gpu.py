@@ -158,11 +158,11 @@ def test_in_place_weight_edit_is_seen():
     assert (a - b).abs().max().item() > 1e-2
     bias.data = bias.data - 0.5              # storage swap: new data_ptr
     c = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
-    assert torch.equal(a, c)
+    assert (a - c).abs().max().item() < 1e-5  # (x + 0.5) - 0.5 differs from x by an fp32 rounding
     bias.data.add_(0.5)                      # in place THROUGH .data: invisible to autograd's counters ...
     net.refresh()                            # ... so the documented call is needed
     d = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
-    assert torch.equal(b, d)
+    assert (b - d).abs().max().item() < 1e-5 and (c - d).abs().max().item() > 1e-2
 
 
 def test_get_featmaps_does_not_touch_forward_tables():
