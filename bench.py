@@ -262,7 +262,7 @@ def extra_single_gpu(net, dev, args, pk):
 
 
 def extra_multi_gpu(net, dev, world, rank, pk, tmax, barrier):
-    """N > 1: the two schedules of north-star item (4) that exchange data between GPUs, with parity fields.
+    """Every N (at N = 1 without the exchange): the two schedules of north-star item (4) that exchange data between GPUs, with parity fields.
     cfg3: a scene of 1024 query frames sharing ONE set of 5 references (reference views sharded over the ranks, K/V of
     both decoder layers exchanged once over NCCL, then queries shard).  cfg4: 1 query x 64 references, reference
     tokens sharded (split-KV cross-attention; partial O + LSE merged per decoder layer over NVLink peer memory or
@@ -291,13 +291,18 @@ def extra_multi_gpu(net, dev, world, rank, pk, tmax, barrier):
         barrier()
         ms_cache = tmax(e0.elapsed_time(e1))
         n_batches = (hi - lo + Bq - 1) // Bq
+        # a rank's share of the scene is only a few batches at N = 8 (35 ms): repeat it so the clocks are in their
+        # steady state for the timed region, report the time of ONE pass over the scene
+        reps = max(1, -(-16 // max(n_batches, 1)))
+        for _ in range(n_batches):
+            sc.score(q_mine)
         barrier()
         e0.record()
-        for _ in range(n_batches):
+        for _ in range(reps * n_batches):
             s = sc.score(q_mine)
         e1.record()
         barrier()
-        ms_score = tmax(e0.elapsed_time(e1))
+        ms_score = tmax(e0.elapsed_time(e1)) / reps
         # parity: the same 4 queries through the plain forward (every query carries its own copy of the references)
         want = net(q_mine[:4], refs[None].expand(4, -1, -1, -1, -1).contiguous(), False, 0, False)["score_map_ref_cross"]
         d3 = tmax(float((sc.score(q_mine[:4]) - want).abs().max()))
@@ -314,7 +319,7 @@ def extra_multi_gpu(net, dev, world, rank, pk, tmax, barrier):
         q1, r64 = (t.to(dev) for t in make_inputs(1, 64, H, W, seed=9))
         c4 = {"workload": f"cfg4: 1 query x 64 refs, {H}x{W}; reference views sharded over {world} GPUs (split-KV)"}
         got = None
-        for mode in ("p2p", "nccl"):
+        for mode in (("p2p", "nccl") if world > 1 else ("nccl",)):
             sk = SplitKVScorer(eng, dev, exchange=mode)
             g = sk.forward(q1, r64).clone()
             got = g if got is None else got
@@ -338,6 +343,9 @@ def extra_multi_gpu(net, dev, world, rank, pk, tmax, barrier):
         c4["ms_per_query_one_gpu"] = tmax(one)
         best = min(v for k, v in c4.items() if k.startswith("ms_per_query_") and k != "ms_per_query_one_gpu")
         c4["speedup_vs_one_gpu"] = c4["ms_per_query_one_gpu"] / best
+        if world == 1:
+            c4["note"] = "one GPU: the split-KV schedule degenerates to a single part (no exchange); ms_per_query_nccl " \
+                         "is that schedule, ms_per_query_one_gpu the plain forward"
         c4["parity"] = {"max_abs_vs_one_gpu": tmax(float((full - got).abs().max())), "max_over": "ranks"}
         out["cfg4"] = c4
     return out
@@ -475,10 +483,9 @@ def run_ours(args):
     # ---- the other BASELINE configs (kept out of the headline numbers above) ----------------------------------
     extra = {}
     if not args.no_extra:
-        if world > 1:
-            extra = extra_multi_gpu(net, dev, world, rank, pk, max_over_ranks, barrier)
-        else:
-            extra = extra_single_gpu(net, dev, args, pk)
+        extra = extra_multi_gpu(net, dev, world, rank, pk, max_over_ranks, barrier)  # cfg3 / cfg4 at every N
+        if world == 1:
+            extra.update(extra_single_gpu(net, dev, args, pk))
 
     if rank != 0:
         if world > 1:

@@ -33,6 +33,7 @@ SIGNATURES = {
     "xs_pos_embed_resample_bicubic_steps": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "xs_gemm_bias_act": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "xs_gemm_bias_residual": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "xs_gemm_bias_residual_ln": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _p, _f, _p, _i, _i, _i, _i, _i, _p]),
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_attn_set_optimistic": (None, [_i]),
     "xs_lse_merge": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _i, _p]),

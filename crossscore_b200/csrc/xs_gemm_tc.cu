@@ -52,7 +52,7 @@ struct JigsawParams {
   float power;
 };
 
-template <int BN, int STAGES, int EPI, int CTA2 = 0, int OUT = 0>
+template <int BN, int STAGES, int EPI, int CTA2 = 0, int OUT = 0, int LNF = 0>
 struct GemmSmem {
   // one 32-row x 32-column staging tile of an epilogue warp (64-byte rows for bf16 output, 128-byte rows for fp32)
   static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * ((OUT == 1 || OUT == 2) ? 4 : 2);
@@ -65,7 +65,10 @@ struct GemmSmem {
   static constexpr uint32_t OFF_STAGING = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_BAR = (OFF_STAGING + STAGING_BYTES + 15u) & ~15u;
   static constexpr uint32_t BAR_BYTES = (2 * STAGES + 4 + 2 * GEMM_KB_MAX + 16) * 8 + 16;  // +16: residual-tile barriers
-  static constexpr uint32_t TOTAL = OFF_BAR + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment of the base
+  static constexpr uint32_t OFF_LNX = (OFF_BAR + BAR_BYTES + 15u) & ~15u;  // LNF: [2 row blocks][8 warps][32 rows] float2
+  static constexpr uint32_t LNX_BYTES = LNF ? 2 * 8 * 32 * 8 : 0;
+  static constexpr uint32_t TOTAL = OFF_LNX + LNX_BYTES + 1024;  // +1024: manual 1 KB alignment of the base
+  static_assert(TOTAL <= 232448, "shared memory layout exceeds 227 KB");
 };
 
 // CTA2 = 1: CTA pairs (cluster of 2, tcgen05 cta_group::2).  One MMA covers a 256 x BN tile: CTA r of the pair
@@ -77,12 +80,28 @@ struct GemmSmem {
 // stay in shared memory while the pair walks ALL n-tiles of that row block, so only W (half a tile per CTA) is
 // streamed.  Per 128 x BN output tile a CTA then pulls BN/2 x 384 x 2 bytes from L2 (74 KB at BN = 192) instead
 // of 240 KB, which moves the K = 384 GEMMs from the L2 -> SM bandwidth bound to the MMA / epilogue bound.
-template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2>
+// LNF = 1 (OUT_F32_ADD, N = 2 n-tiles): the LayerNorm that follows the residual add is fused into the epilogue.  A CTA
+// walks BOTH n-tiles of its 128 rows (row-block-major order in every operand mode), so after the second tile's
+// residual update it knows the statistics of the full 384-wide rows; it then re-reads the rows it has just stored
+// (its own TMA stores, L2 hits) tile by tile, normalises and emits y = LN(h) in bf16 through a second tensor map.
+// The LayerNorm kernel launch and its HBM read of h disappear (modeling_dinov2.py:367-386: norm2 after the attention
+// residual, the next layer's norm1 after the MLP residual).
+struct LnParams {
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const float* h;       // the residual stream the epilogue has just updated (row pitch ldh floats)
+  __nv_bfloat16* y;     // LayerNorm output (row pitch ldy elements)
+  int ldh, ldy;
+};
+
+template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2, int LNF = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
-               JigsawParams jp) {
-  using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY,
+               const float* __restrict__ bias, int M, int N, int K, JigsawParams jp, LnParams lnp) {
+  using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT, LNF>;
+  static_assert(!LNF || (OUT == OUT_F32_ADD && EPI == EPI_STORE && BN == 192), "LN fusion: residual epilogue only");
   static_assert(!CTA2 || (IN == IN_BF16 && EPI == EPI_STORE), "CTA pairs: bf16 store epilogue only");
   constexpr int NC = CTA2 ? 2 : 1;                       // CTAs per tile
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader
@@ -103,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* res_full = a_empty + GEMM_KB_MAX;   // [8 epilogue warps][2] OUT_F32_ADD only: residual tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
   constexpr bool ASTAT = CTA2 == 2;
+  constexpr bool ROWMAJOR = ASTAT || LNF;  // a worker walks whole row blocks (all n-tiles) instead of single tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,12 +135,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // tile sequence of this worker: streaming modes walk tiles worker, worker + n_workers, ... (n fastest);
   // the A-stationary mode walks row blocks worker, worker + n_workers, ... and all n-tiles inside each
   const int my_rounds = worker < num_m ? (num_m - worker + n_workers - 1) / n_workers : 0;
-  const int my_count = ASTAT ? my_rounds * num_n : (worker < num_tiles ? (num_tiles - worker + n_workers - 1) / n_workers : 0);
+  const int my_count = ROWMAJOR ? my_rounds * num_n : (worker < num_tiles ? (num_tiles - worker + n_workers - 1) / n_workers : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     if constexpr (EPI == EPI_STORE) tma_prefetch_desc(&tmC);
+    if constexpr (LNF) tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -179,8 +200,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     } else
-    for (int tile = worker; tile < num_tiles; tile += n_workers) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int t = 0; t < my_count; ++t) {
+      const int tile = ROWMAJOR ? 0 : worker + t * n_workers;
+      const int m_blk = ROWMAJOR ? worker + (t / num_n) * n_workers : tile / num_n;
+      const int n_blk = ROWMAJOR ? t % num_n : tile % num_n;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
@@ -238,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     } else
-    for (int tile = worker; tile < num_tiles; tile += n_workers) {
+    for (int t = 0; t < my_count; ++t) {
       mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tb + acc_stage * ACC_STAGE_COLS;
@@ -279,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (row block, n-tile) of this worker's t-th tile
     auto tile_coords = [&](int t, int& m_blk_o, int& n_blk_o) {
       int m_tile;
-      if constexpr (ASTAT) {
+      if constexpr (ROWMAJOR) {
         m_tile = worker + (t / num_n) * n_workers;
         n_blk_o = t % num_n;
       } else {
@@ -298,7 +321,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto issue_res_load = [&](uint32_t step_idx) {  // one lane
       if constexpr (OUT == OUT_F32_ADD && EPI == EPI_STORE) {
         constexpr int MY_STEPS_ = BN / 64;
-        const int t = static_cast<int>(step_idx / MY_STEPS_), sidx = static_cast<int>(step_idx % MY_STEPS_);
+        int t, sidx;
+        if constexpr (LNF) {
+          // per row block: pass 1 = the residual tiles of its num_n * MY_STEPS_ steps, pass 2 = the same tiles again
+          // (now holding h + delta, written by this warp's own TMA stores)
+          const int spr = num_n * MY_STEPS_;
+          const int rb = static_cast<int>(step_idx) / (2 * spr), s2 = static_cast<int>(step_idx) % spr;
+          t = rb * num_n + s2 / MY_STEPS_;
+          sidx = s2 % MY_STEPS_;
+        } else {
+          t = static_cast<int>(step_idx / MY_STEPS_);
+          sidx = static_cast<int>(step_idx % MY_STEPS_);
+        }
         if (t >= my_count) return;
         int mb, nb;
         tile_coords(t, mb, nb);
@@ -311,9 +345,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (OUT == OUT_F32_ADD && EPI == EPI_STORE) {
       if (lane == 0) issue_res_load(0);
     }
+    // LNF: shifted sums of this thread's half of the row (192 of 384 columns) over the row block's n-tiles
+    float ln_c = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;
+    float2* ln_x = reinterpret_cast<float2*>(smem + L::OFF_LNX);
     for (int i = 0; i < my_count; ++i) {
       int m_blk, n_blk;
       tile_coords(i, m_blk, n_blk);
+      const int row_block = i / num_n;  // (the step loop below reuses the name i)
+      (void)row_block;
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + acc_stage * ACC_STAGE_COLS + (static_cast<uint32_t>(q * 32) << 16);
@@ -349,6 +388,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // step's residual tile into it; then wait for this step's tile (requested one step ago)
             if (lane == 0) {
               tma_store_wait_read<0>();
+              if constexpr (LNF) {
+                // the next load may be a pass-2 load (last pass-1 step of the row block): the tile it re-reads was
+                // stored 2 * num_n * MY_STEPS - 1 steps ago; at most 4 younger store groups may still be pending
+                if (n_blk == num_n - 1 && i == MY_STEPS - 1) tma_store_wait_all<4>();
+              }
               issue_res_load(chunk_counter + 1);
             }
             mbar_wait(&my_res_full[buf], (chunk_counter >> 1) & 1);
@@ -396,6 +440,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 r4 = *sp;
                 o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
               }
+              if constexpr (LNF) {
+                if (n_blk == 0 && i == 0 && j == 0) {  // first value of the row block: the shift of the running sums
+                  ln_c = o4.x;
+                  ln_s1 = 0.f;
+                  ln_s2 = 0.f;
+                }
+                const float d0 = o4.x - ln_c, d1 = o4.y - ln_c, d2 = o4.z - ln_c, d3 = o4.w - ln_c;
+                ln_s1 += (d0 + d1) + (d2 + d3);
+                ln_s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+              }
               *sp = o4;
             }
           }
@@ -405,6 +459,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // box = 32 columns x 32 rows; clips the M tail
             tma_store_2d(&tmC, srow, n0, m0);
             tma_store_commit();
+          }
+        }
+        if constexpr (LNF) {
+          if (n_blk == num_n - 1) {
+            // ---- statistics of the full rows: this warp saw COLS_HALF columns of each of its 32 rows, the other warp
+            //      of the lane quarter the rest.  Chan's parallel update of (mean, M2) merges the two halves. ----
+            const float nh = static_cast<float>(num_n * (BN / 2));
+            const float mean_t = ln_c + ln_s1 / nh;
+            const float m2_t = ln_s2 - ln_s1 * ln_s1 / nh;
+            const int rbp = row_block & 1;
+            ln_x[(rbp * 8 + (warp - 4)) * 32 + lane] = make_float2(mean_t, m2_t);
+            named_bar_sync(2 + q, 64);  // the two warps of this lane quarter
+            const float2 other = ln_x[(rbp * 8 + ((warp - 4) ^ 4)) * 32 + lane];
+            const float dm = other.x - mean_t;
+            const float mean = mean_t + 0.5f * dm;
+            const float var = (m2_t + other.y + dm * dm * (0.5f * nh)) / (2.0f * nh);
+            const float rstd = rsqrtf(var + lnp.eps);
+            // ---- pass 2: re-read the updated tiles (this warp's own TMA stores: L2 hits) through the same
+            //      double-buffered TMA pipeline, normalise, store y (bf16) through the second tensor map.
+            //      (A variant with plain per-thread vector loads instead of TMA was 2x slower: thread == row makes every
+            //      lane touch its own cache line.  profiles/r2_experiments.txt) ----
+#pragma unroll 1
+            for (int s2 = 0; s2 < num_n * MY_STEPS; ++s2) {
+              const int nb2 = s2 / MY_STEPS, c2 = 2 * (s2 % MY_STEPS) + half;
+              const uint32_t buf = chunk_counter & 1;
+              if (lane == 0) {
+                tma_store_wait_read<0>();
+                // next load: another pass-2 tile (its store has at most 4 younger groups) or the next row block's
+                // first residual tile (no dependence)
+                if (s2 + 1 < num_n * MY_STEPS) tma_store_wait_all<4>();
+                issue_res_load(chunk_counter + 1);
+              }
+              mbar_wait(&my_res_full[buf], (chunk_counter >> 1) & 1);
+              __syncwarp();
+              ++chunk_counter;
+              const int n0 = nb2 * BN + c2 * 32;
+              uint8_t* srow = my_staging + buf * L::WARP_STAGE_BYTES;
+              const float4* g4 = reinterpret_cast<const float4*>(lnp.gamma + n0);
+              const float4* b4l = reinterpret_cast<const float4*>(lnp.beta + n0);
+              uint32_t pk[16];
+              const uint8_t* rp = srow + lane * 128;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 x4 = *reinterpret_cast<const float4*>(rp + ((j ^ (lane & 7)) << 4));
+                const float4 g = __ldg(g4 + j), bb = __ldg(b4l + j);
+                pk[2 * j] = pack_bf16x2((x4.x - mean) * rstd * g.x + bb.x, (x4.y - mean) * rstd * g.y + bb.y);
+                pk[2 * j + 1] = pack_bf16x2((x4.z - mean) * rstd * g.z + bb.z, (x4.w - mean) * rstd * g.w + bb.w);
+              }
+              __syncwarp();  // every lane has read its fp32 row before the bf16 rows overwrite the buffer
+              uint8_t* wp = srow + lane * 64;  // 64-byte rows, 64B swizzle (the layout of the bf16 output tensor map)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(wp + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmY, srow, n0, m0);
+                tma_store_commit();
+              }
+            }
           }
         }
       } else {
@@ -476,10 +591,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2 = 0>
+template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2 = 0, int LNF = 0>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
-                       int N, int K, JigsawParams jp, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT>;
+                       int N, int K, JigsawParams jp, cudaStream_t stream, void* y = nullptr, int ldy = 0,
+                       LnParams lnp = LnParams{nullptr, nullptr, 0.f, nullptr, nullptr, 0, 0}) {
+  using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT, LNF>;
   constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
   constexpr int OUT_B = (OUT == OUT_F32 || OUT == OUT_F32_ADD) ? 4 : 2;
   constexpr uint32_t BKE = 128 / IN_B;
@@ -507,11 +623,19 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
   } else {
     tmC = tmA;  // unused
   }
-  auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT, IN, OUT, CTA2>;
+  CUtensorMap tmY = tmC;  // unused unless LNF
+  if constexpr (LNF) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)ldy * 2};
+    uint32_t box[2] = {32, 32};
+    int rc = make_tmap(&tmY, y, 2, 2, dims, strides, box, SWZ_64B);
+    if (rc) return rc;
+  }
+  auto kern = gemm_tc_kernel<BN, STAGES, EPI, ACT, IN, OUT, CTA2, LNF>;
   XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::TOTAL));
   if constexpr (CTA2) {
     const int num_m2 = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-    const int units = CTA2 == 2 ? num_m2 : num_m2 * (N / BN);  // A-stationary pairs walk whole row blocks
+    const int units = (CTA2 == 2 || LNF) ? num_m2 : num_m2 * (N / BN);  // row-block-major modes walk whole row blocks
     const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
@@ -525,11 +649,11 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    XS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmC, bias, M, N, K, jp));
+    XS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmC, tmY, bias, M, N, K, jp, lnp));
   } else {
-    const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
+    const int num_tiles = LNF ? (M + GEMM_BM - 1) / GEMM_BM : ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmW, tmC, bias, M, N, K, jp);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmW, tmC, tmY, bias, M, N, K, jp, lnp);
   }
   XS_LAUNCH_CHECK();
   return 0;
@@ -595,18 +719,12 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
   if (!in_tf32 && !out_f32) {
     // CTA pairs for the long-K GEMM (fc2, K = 1536: 1.35 PF vs 1.13 PF single-CTA, measured); the K = 384 GEMMs
     // are bound by their epilogue / operand refill per tile and run faster as independent CTAs.
-    // XS_GEMM_PAIR=0 / 2 forces the single-CTA / streaming-pair kernel (3: no A-stationary mode).
-    static int pair_mode = -1;
-    if (pair_mode < 0) {
-      const char* e = getenv("XS_GEMM_PAIR");
-      pair_mode = e ? atoi(e) : 1;
-    }
     const int bn = use192 ? 192 : 256;
     const int num_m2 = (M + 255) / 256;
     const bool fits = num_m2 * (N / bn) >= num_sms() / 2;
-    const bool pair = fits && (pair_mode == 2 || ((pair_mode == 1 || pair_mode == 3) && K >= 1024));
+    const bool pair = fits && K >= 1024;
     // K <= 384 (qkv, proj, fc1): A-stationary pairs once every pair of SMs has a 256-row block of its own
-    const bool astat = pair_mode == 1 && K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2;
+    const bool astat = K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2;
     if (astat) {
       if (use192) return dispatch_act<192, 8, IN_BF16, OUT_BF16, 2>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
       return dispatch_act<256, 6, IN_BF16, OUT_BF16, 2>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
@@ -625,16 +743,11 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
     // by TMA), so the delta never exists in HBM and the LayerNorm that follows reads the residual stream only
     XS_CHECK_ARG(act == ACT_NONE, "gemm: residual accumulate supports act=NONE only");
     XS_CHECK_ARG(use192, "gemm: residual accumulate needs N %% 192 == 0 (N=%d)", N);
-    static int pair_mode = -1;
-    if (pair_mode < 0) {
-      const char* e = getenv("XS_GEMM_PAIR");
-      pair_mode = e ? atoi(e) : 1;
-    }
     const int num_m2 = (M + 255) / 256;
     const bool fits = num_m2 * (N / 192) >= num_sms() / 2;
-    if (pair_mode == 1 && K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
+    if (K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
       return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 2>(XS_GEMM_ARGS);
-    if (pair_mode != 0 && fits && K >= 1024)
+    if (fits && K >= 1024)
       return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 1>(XS_GEMM_ARGS);
     return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD>(XS_GEMM_ARGS);
   }
@@ -652,6 +765,31 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
   XS_CHECK_ARG(act == ACT_NONE, "gemm: tf32->bf16 supports act=NONE only");
   if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_TF32, OUT_BF16>(XS_GEMM_ARGS);
   return launch_gemm<256, 3, EPI_STORE, ACT_NONE, IN_TF32, OUT_BF16>(XS_GEMM_ARGS);
+}
+
+// h (fp32, in place) += A W^T + bias, then y (bf16) = LayerNorm(h; gamma, beta, eps) in the same kernel.
+// Returns 1 when the shape is not covered by the fused kernel (the caller then runs the two steps separately).
+int gemm_tc_residual_ln(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
+                        const float* gamma, const float* beta, float eps, void* y, int ldy, int M, int N, int K,
+                        cudaStream_t stream) {
+  XS_CHECK_ARG(M > 0 && K > 0, "gemm_residual_ln: empty problem");
+  XS_CHECK_ARG((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && (ldh % 4) == 0 && (ldy % 8) == 0,
+               "gemm_residual_ln: row pitches must be multiples of 16 bytes");
+  XS_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(h) |
+                 reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(gamma) |
+                 reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+               "gemm_residual_ln: pointers must be 16-byte aligned");
+  if (N != 384) return 1;  // the fused epilogue needs the whole row in one CTA: two 192-wide n-tiles
+  const int num_m2 = (M + 255) / 256;
+  JigsawParams jp{};
+  void* out = h;
+  const int ldc = ldh;
+  const LnParams lnp{gamma, beta, eps, h, static_cast<__nv_bfloat16*>(y), ldh, ldy};
+  if (K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
+    return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 2, 1>(XS_GEMM_ARGS, y, ldy, lnp);
+  if (K >= 1024 && num_m2 >= num_sms() / 2)
+    return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 1, 1>(XS_GEMM_ARGS, y, ldy, lnp);
+  return 1;
 }
 
 // head.2 Linear (384 -> 196, weight rows padded to 224) + sigmoid/tanh (+pow) + jigsaw scatter

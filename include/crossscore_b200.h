@@ -117,6 +117,15 @@ int xs_gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float
 int xs_gemm_bias_residual(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
                           int M, int N, int K, int dtype, xs_stream_t stream);
 
+/* K6+K2, K7+K2  the same residual update followed by the LayerNorm the reference applies next
+ *     (modeling_dinov2.py:367-386: norm2 after the attention residual; the next layer's norm1 after the MLP residual):
+ *         h (fp32, in place) += A @ W^T + bias;   y (bf16) = LayerNorm(h; gamma, beta, eps)
+ *     in ONE kernel when there are enough rows to fill the GPU (the CTA that updates a 128-row block re-reads it from
+ *     L2 and emits y; no LayerNorm launch, no HBM read of h), otherwise as the two launches it replaces.  N = 384. */
+int xs_gemm_bias_residual_ln(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
+                             const float* gamma, const float* beta, float eps, void* y, int ldy, int M, int N, int K,
+                             int dtype, xs_stream_t stream);
+
 /* K4,K9,K10  O = softmax(Q K^T * scale) V  per (batch, head), no mask
  *     (modeling_dinov2.py:203-234; $SP/torch/nn/functional.py:6630-6692 via transformer.py:182-205).
  *     head_slot: column pitch between heads in q/k/v rows (bf16: must be 64).  kv_shared: all batches

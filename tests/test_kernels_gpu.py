@@ -153,6 +153,30 @@ def test_gemm_bias_residual(M, N, K):
         call("xs_gemm_bias_residual", P(A), K, P(W), K, P(b), P(h), N, M, N, K, DT_F32, st())
 
 
+@pytest.mark.parametrize("M,K", [(20000, 384), (19001, 384), (20000, 1536), (37931, 1536), (1000, 384), (9000, 1536)])
+def test_gemm_bias_residual_ln(M, K):
+    """h += A W^T + b and y = LayerNorm(h) in one kernel (fused epilogue for M large enough to fill the GPU: CTA pairs,
+    A-stationary for K = 384 and streaming for K = 1536; ragged row tails; the small shapes take the two-launch path).
+    Rows carry a large common offset and a few outlier channels: the statistics are merged from two half rows."""
+    N = 384
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+    b = rnd(N, seed=3)
+    h0 = rnd(M, N, seed=4, scale=2.0) + 7.0
+    h0[:, [5, 133, 301]] *= 40.0
+    g, be = rnd(N, seed=5) * 0.2 + 1, rnd(N, seed=6, scale=0.1)
+    h = h0.clone()
+    y = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call("xs_gemm_bias_residual_ln", P(A), K, P(W), K, P(b), P(h), N, P(g), P(be), 1e-6, P(y), N, M, N, K, DT_BF16, st())
+    torch.cuda.synchronize()
+    href = h0.double() + A.double() @ W.double().T + b.double()
+    assert ((h.double() - href).abs() <= 2e-3 + 1e-5 * href.abs()).all()
+    yref = torch.nn.functional.layer_norm(href, (N,), g.double(), be.double(), 1e-6)
+    err = (y.double() - yref).abs()
+    assert torch.isfinite(y).all()
+    assert (err <= 0.02 + 0.01 * yref.abs()).all(), err.max().item()
+
+
 def test_gemm_bf16_rejects_bad_shapes():
     A = rnd(128, 384, dtype=torch.bfloat16)
     W = rnd(200, 384, dtype=torch.bfloat16)
