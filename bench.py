@@ -134,7 +134,9 @@ def run_reference(args):
         return
     steps = max(1, args.steps)
     rate, sec, cores, n = cpu_oracle_rate(steps, min(args.warmup, 1))
-    sample = f"{n} forwards of cfg-1 (1 query + {N_REF} refs, {H}x{W}, fp32 CPU oracle port on torch fused CPU ops), {sec:.2f} s each"
+    sample = (f"{n} forwards of cfg-1 (1 query + {N_REF} refs, {H}x{W}), fp32, oracle port of the reference on torch's fused CPU "
+              f"ops (F.linear / SDPA / layer_norm / gelu: the calls the reference makes; within 5 % of the reference itself "
+              f"on the build container, DESIGN.md section 6), {sec:.2f} s each; batch 1 because a batch-32 step takes ~40 s")
     line = {
         "impl": "reference", "metric": "score maps/s (518x518, 5 refs)", "value": rate, "unit": "maps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
@@ -187,7 +189,7 @@ def profile_kernels(net, dev, fn, pk):
         if fl > 0:
             ent["tflops"] = round(fl / (ms * 1e-3) / 1e12, 2)
             ent["frac_of_tensor_peak_sustained"] = round(ent["tflops"] / pk["tensor_sustained"], 4)
-        elif nb > 0:
+        if nb > 0:  # HBM-bound kernels (LayerNorm, PE add, head + jigsaw: SURVEY 8d) report GB/s against the HBM peak
             ent["gbs"] = round(nb / (ms * 1e-3) / 1e9, 1)
             ent["frac_of_hbm_peak"] = round(ent["gbs"] / pk["hbm"], 4)
         kernels[tag] = ent
@@ -497,8 +499,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         rate, sec, cores, n = cpu_oracle_rate(2, 1)
         cpu = {"value": rate, "unit": "maps/s", "cores": cores, "kind": "port",
-               "sample": f"{n} forwards of cfg-1 (1 query + {N_REF} refs, {H}x{W}), fp32 CPU oracle port on torch fused CPU ops, "
-                         f"{sec:.2f} s each, after 1 warm-up"}
+               "sample": f"{n} forwards of cfg-1 (1 query + {N_REF} refs, {H}x{W}), fp32, oracle port of the reference on torch's "
+                         f"fused CPU ops (within 5 % of the reference itself on the build container), {sec:.2f} s each, after 1 "
+                         f"warm-up; batch 1 because a batch-32 step takes ~12 s per forward"}
 
     fpm = flops_per_map()
     line = {

@@ -44,6 +44,29 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
+def attn_kv_splits(tiles: int, nblk: int, slots: int = 2 * NUM_SMS_HINT, max_splits: int = 8) -> int:
+    """How many key ranges a flash-attention launch is cut into (partials merged by xs_lse_merge).
+
+    The kernel is persistent with `slots` CTAs (two per SM) walking `tiles * nsplit` equally long tiles, so its
+    efficiency is tiles*nsplit / (ceil(tiles*nsplit / slots) * slots).  Few tiles (a single query: 8 heads x 11 query
+    tiles = 88) leave most SMs idle, and a tile count just above a multiple of `slots` (cfg 5's cross-attention: 344
+    tiles on 296 slots) pays a nearly empty second wave -- both are fixed by splitting the keys.  A split costs an fp32
+    partial-output round trip and the merge launch, so it has to buy at least 8 % and every range keeps >= 4 key blocks
+    of 128."""
+    best, best_eff = 1, 0.0
+    for n in range(1, max(1, min(max_splits, nblk // 4)) + 1):
+        per = -(-nblk // n)
+        if -(-nblk // per) != n:  # every split must own at least one key block
+            continue
+        work = tiles * n
+        eff = work / (-(-work // slots) * slots)
+        if n == 1:
+            best, best_eff = 1, eff
+        elif eff > best_eff + 0.08:
+            best, best_eff = n, eff
+    return best
+
+
 POS_INTERP_MODES = ("scale_factor", "size")
 
 
@@ -292,11 +315,7 @@ class Engine:
         """q/k/v are tensor views whose data_ptr is the first column of the respective part; o is bf16 or
         fp32 (B*Lq, heads*d)."""
         scale = self.attn_scale(d)
-        ctas = B * heads * ((Lq + 127) // 128)
-        nblk = (Lk + 127) // 128
-        nsplit = max(1, min((2 * NUM_SMS_HINT) // max(ctas, 1), nblk // 4))
-        per = -(-nblk // nsplit)
-        nsplit = -(-nblk // per)  # every split owns at least one key block
+        nsplit = attn_kv_splits(B * heads * ((Lq + 127) // 128), (Lk + 127) // 128)
         o_is_f32 = 1 if o.dtype == torch.float32 else 0
         flops = 4.0 * B * heads * Lq * Lk * d  # QK^T + PV
         if nsplit == 1:

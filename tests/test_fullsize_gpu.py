@@ -137,3 +137,19 @@ def test_cfg4_split_kv_schedule_vs_reference_golden(precision):
     tmax, tmean = (1e-2, 1e-3) if precision == "bf16" else (1e-4, 2e-5)
     assert mx <= tmax and mean <= tmean, (mx, mean)
     assert (score - plain).abs().max().item() <= (5e-3 if precision == "bf16" else 1e-5)
+
+
+def test_fused_layernorm_plan_matches_default(monkeypatch):
+    """XS_FUSE_LN=1 (residual add + the following LayerNorm in the GEMM epilogue, xs_gemm_bias_residual_ln) against the
+    default plan at a size where the fused kernel really runs (14 images x 1370 tokens = 19 180 rows >= 74 row-block
+    pairs): the only difference is the bf16 rounding point of y, so the maps agree far inside the bf16 tolerance."""
+    q, r = make_inputs(2, 6, 518, 518, seed=31)
+    q, r = q.to(DEV), r.to(DEV)
+    monkeypatch.setenv("XS_FUSE_LN", "0")
+    a = _net(seed=2)(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    monkeypatch.setenv("XS_FUSE_LN", "1")
+    net = _net(seed=2)
+    assert net._engine(DEV).fuse_ln
+    b = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    d = (a - b).abs()
+    assert d.max().item() <= 5e-3 and d.mean().item() <= 5e-4, (d.max().item(), d.mean().item())

@@ -99,3 +99,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_attention_key_split_heuristic():
+    """Engine picks the number of key ranges from the wave efficiency of the persistent attention kernel."""
+    from crossscore_b200.engine import attn_kv_splits
+    assert attn_kv_splits(192 * 6 * 11, 11) == 1        # cfg 2 DINOv2 attention: 42.8 waves, nothing to gain
+    assert attn_kv_splits(32 * 8 * 11, 54) == 1         # cfg 2 cross-attention
+    assert attn_kv_splits(88, 685) == 3                 # one query: 88 tiles -> 264 on 296 slots
+    assert attn_kv_splits(8 * 43, 685) == 5             # cfg 5 cross-attention: 344 tiles = 1.16 waves -> 5.8 waves
+    assert attn_kv_splits(88, 3) == 1                   # too few key blocks to split
+    for tiles, nblk in [(1, 1), (7, 9), (300, 40), (5000, 2)]:
+        n = attn_kv_splits(tiles, nblk)
+        per = -(-nblk // n)
+        assert 1 <= n <= 8 and (n - 1) * per < nblk     # every range owns at least one key block
