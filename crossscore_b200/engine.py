@@ -47,23 +47,21 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
 def attn_kv_splits(tiles: int, nblk: int, slots: int = 2 * NUM_SMS_HINT, max_splits: int = 8) -> int:
     """How many key ranges a flash-attention launch is cut into (partials merged by xs_lse_merge).
 
-    The kernel is persistent with `slots` CTAs (two per SM) walking `tiles * nsplit` equally long tiles, so its
-    efficiency is tiles*nsplit / (ceil(tiles*nsplit / slots) * slots).  Few tiles (a single query: 8 heads x 11 query
-    tiles = 88) leave most SMs idle, and a tile count just above a multiple of `slots` (cfg 5's cross-attention: 344
-    tiles on 296 slots) pays a nearly empty second wave -- both are fixed by splitting the keys.  A split costs an fp32
-    partial-output round trip and the merge launch, so it has to buy at least 8 % and every range keeps >= 4 key blocks
-    of 128."""
-    best, best_eff = 1, 0.0
+    The kernel is persistent with `slots` CTAs (two per SM) walking `tiles * nsplit` equally long tiles, so a launch takes
+    ceil(tiles * nsplit / slots) waves of (tile time / nsplit).  Few tiles (a single query: 8 heads x 11 query tiles = 88)
+    leave most SMs idle, and a tile count just above a multiple of `slots` (cfg 5's cross-attention: 344 tiles on 296
+    slots) pays a nearly empty second wave -- both are fixed by splitting the keys.  A split costs an fp32 partial-output
+    round trip and the merge launch (~15 us, measured), so short launches (the DINOv2 attention of a handful of images:
+    8 us per tile) are left alone.  Tile time: ~0.8 us per 128 keys (measured: 570 clk per 64-key block at ~1.5 GHz)."""
+    t_tile = 0.8 * nblk  # microseconds
+    best, best_t = 1, None
     for n in range(1, max(1, min(max_splits, nblk // 4)) + 1):
         per = -(-nblk // n)
         if -(-nblk // per) != n:  # every split must own at least one key block
             continue
-        work = tiles * n
-        eff = work / (-(-work // slots) * slots)
-        if n == 1:
-            best, best_eff = 1, eff
-        elif eff > best_eff + 0.08:
-            best, best_eff = n, eff
+        t = -(-tiles * n // slots) * t_tile / n + (15.0 if n > 1 else 0.0)
+        if best_t is None or t < best_t * 0.97:  # prefer fewer splits on near-ties
+            best, best_t = n, t
     return best
 
 
