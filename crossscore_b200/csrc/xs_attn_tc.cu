@@ -371,14 +371,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float mA = -INFINITY, mB = -INFINITY;  // SAFE: running row maxima (log2 domain)
       float2 lA = make_float2(0.f, 0.f), lB = make_float2(0.f, 0.f);  // per-thread partial row sums
 
+      uint32_t sb = g0 % ATT_NS, ph_s = (g0 / ATT_NS) & 1;  // running S buffer index and barrier phase of the block
       auto block = [&](const int j, auto mask_tag) {
         constexpr bool MASK = decltype(mask_tag)::value;
-        const uint32_t g = g0 + j;
-        const uint32_t sb = g % ATT_NS;
         const uint32_t t_s = tmem_base + lane_off + sb * 64;
         uint32_t v[32], pk[16];
         pc.lap(7);
-        mbar_wait(s_full + (sb), (g / ATT_NS) & 1);
+        mbar_wait(s_full + (sb), ph_s);
         pc.lap(0);
         tc_fence_after();
         if (!(ATT_DBG & 4) || j == 0) tmem_ld_16x256b_x8(t_s, v);
@@ -431,6 +430,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (j > 0 && __any_sync(0xffffffffu, (nA != mA) || (nB != mB))) {
             // O must hold PV of all earlier blocks of this tile: wait for the previous block's PV through its
             // K/V slot's kv_empty phase (the slot is refilled only ATT_ST blocks later: the parity cannot alias)
+            const uint32_t g = g0 + j;
             mbar_wait(kv_empty + ((g - 1) % ATT_ST), ((g - 1) / ATT_ST) & 1);
             tc_fence_after();
 #pragma unroll
@@ -468,8 +468,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         pc.lap(3);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full + sb);
+        if (elect_one_sync()) mbar_arrive(p_full + sb);
         pc.lap(4);
+        if (++sb == ATT_NS) {
+          sb = 0;
+          ph_s ^= 1;
+        }
       };
       for (int j = 0; j + 1 < nkv; ++j) block(j, TagNo{});
       block(nkv - 1, TagYes{});

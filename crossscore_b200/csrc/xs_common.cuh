@@ -262,13 +262,18 @@ __device__ __forceinline__ bool mbar_try_wait_hint(B bar, uint32_t parity) {
 template <class B>
 __device__ __forceinline__ void mbar_wait(B bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // Slow path: every poll parks the warp in hardware (suspend-time hint), so the loop issues three instructions per
+  // wake-up.  The watchdog reads the clock only once per 2^16 polls (>= 1 s of parked time) and traps ~4 s later, so a
+  // pipeline bug fails the launch instead of hanging the GPU box; nothing of it is on the common path.
+  long long t0 = 0;
 #pragma unroll 1
-  for (;;) {
-#pragma unroll 1
-    for (int i = 0; i < 4096; ++i)
-      if (mbar_try_wait_hint(bar, parity)) return;
-    if (clock64() - t0 > 8000000000LL) __trap();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait_hint(bar, parity)) return;
+    if ((spins & 0xFFFFu) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   }
 }
 
