@@ -75,6 +75,7 @@ class SceneScorer:
         self.grid: Optional[Tuple[int, int]] = None
         self.n_ref = 0
         self.cache_bytes_received = 0
+        self._graphs = {}  # query batch shape -> (CUDAGraph, static input, static output)
 
     def build_reference_cache(self, ref_imgs: torch.Tensor) -> torch.Tensor:
         """ref_imgs (N,3,H,W) fp32, identical on every rank.  Encodes this rank's slice of the views, projects
@@ -101,30 +102,67 @@ class SceneScorer:
                     if owner != self.rank:
                         self.cache_bytes_received += rows.numel() * rows.element_size()
         self.kv, self.grid, self.n_ref = kv, (ph, pw), N
+        self._graphs.clear()  # captured graphs hold the previous cache's pointers
         return kv
 
-    def score(self, query_imgs: torch.Tensor) -> torch.Tensor:
-        """query_imgs (Bq,3,H,W): THIS rank's queries -> (Bq, 14ph, 14pw) fp32 score maps."""
+    def score(self, query_imgs: torch.Tensor, graph: bool = False) -> torch.Tensor:
+        """query_imgs (Bq,3,H,W): THIS rank's queries -> (Bq, 14ph, 14pw) fp32 score maps.
+
+        graph=True replays the batch as ONE CUDA graph (captured per batch shape against the current cache): a batch of
+        32 queries is ~115 launches in ~7 ms, so with eager launches the schedule is at the mercy of the host -- eight
+        ranks driving their GPUs from one shared CPU lose 15 % to it (bench.py cfg3).  The returned tensor is the graph's
+        static output: valid until the next graphed call with the same shape."""
         if self.kv is None:
             raise RuntimeError("build_reference_cache() must run before score()")
         Bq, _, H, W = query_imgs.shape
         ph, pw = H // PATCH, W // PATCH
         if (ph, pw) != self.grid:
             raise ValueError(f"query patch grid {(ph, pw)} differs from the cached reference grid {self.grid}")
+        if graph and self.device.type == "cuda":
+            return self._score_graphed(query_imgs)
+        return self._score_eager(query_imgs.contiguous())
+
+    def _score_eager(self, query_imgs: torch.Tensor) -> torch.Tensor:
+        Bq, _, H, W = query_imgs.shape
+        ph, pw = H // PATCH, W // PATCH
         P = ph * pw
         eng, st = self.engine, _stream(self.device)
-        xq32, _ = eng.features(query_imgs.contiguous(), None, st)
+        xq32, _ = eng.features(query_imgs, None, st)
         score, _ = eng.decode(xq32, self.kv, Bq, P, self.n_ref * P, ph, pw, st, kv_shared=True)
         return score
 
-    def score_scene(self, all_query_imgs: torch.Tensor, ref_imgs: torch.Tensor, batch: int = 32) -> torch.Tensor:
+    def _score_graphed(self, query_imgs: torch.Tensor) -> torch.Tensor:
+        key = tuple(query_imgs.shape)
+        ent = self._graphs.get(key)
+        if ent is None:
+            q_static = torch.empty_like(query_imgs, device=self.device).contiguous()
+            q_static.copy_(query_imgs)
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up off the capture: workspaces, tables, lazily created buffers
+                self._score_eager(q_static)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._score_eager(q_static)
+            ent = (g, q_static, out)
+            self._graphs[key] = ent
+        g, q_static, out = ent
+        q_static.copy_(query_imgs, non_blocking=True)
+        g.replay()
+        return out
+
+    def score_scene(self, all_query_imgs: torch.Tensor, ref_imgs: torch.Tensor, batch: int = 32,
+                    graph: bool = False) -> torch.Tensor:
         """Convenience driver: every rank passes the same (Q,3,H,W) queries, scores its contiguous shard in
         batches and returns the shard's maps (rank r owns queries shard_range(Q, world, r))."""
         self.build_reference_cache(ref_imgs)
         lo, hi = shard_range(all_query_imgs.shape[0], self.world, self.rank)
         outs: List[torch.Tensor] = []
         for s in range(lo, hi, batch):
-            outs.append(self.score(all_query_imgs[s:min(hi, s + batch)]).clone())
+            outs.append(self.score(all_query_imgs[s:min(hi, s + batch)], graph=graph).clone())
         if not outs:
             H, W = all_query_imgs.shape[-2:]
             return torch.empty(0, PATCH * (H // PATCH), PATCH * (W // PATCH), device=self.device)

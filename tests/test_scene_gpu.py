@@ -49,6 +49,28 @@ def test_scene_cache_single_gpu(precision):
     assert err.max().item() <= TOL[precision][0] and err.mean().item() <= TOL[precision][1]
 
 
+def test_scene_scorer_graph_replay_matches_eager():
+    """score(graph=True) replays the batch as one CUDA graph: same bits as the eager launches, for new inputs of the same
+    shape, for a second batch shape, and after the reference cache has been rebuilt (graphs are dropped with it)."""
+    sd, q, refs = _problem(3, 6)
+    dev = torch.device("cuda", 0)
+    eng = _net(sd, "bf16", dev)._engine(dev)
+    sc = SceneScorer(eng, dev)
+    sc.build_reference_cache(refs.to(dev))
+    q = q.to(dev)
+    for batch in (q[:4], q[2:6], q[:2], q[:4]):
+        want = sc.score(batch).clone()
+        got = sc.score(batch, graph=True).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    _, refs2 = make_inputs(1, 3, H, W, seed=44)
+    sc.build_reference_cache(refs2[0].to(dev))
+    want = sc.score(q[:4]).clone()
+    got = sc.score(q[:4], graph=True).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_split_kv_single_gpu(precision):
     sd, q, refs = _problem(4, 2)
