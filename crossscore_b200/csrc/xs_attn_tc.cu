@@ -43,8 +43,9 @@ constexpr int ATT_NS = 3;                               // S buffers in TMEM (QK
 // In-run A/B on the DINOv2 shape (192 images, profiles/r2_attn_experiments.txt): 0/16 0.857 ms, 3/16 0.741, 4/16 0.699,
 // 5/16 0.699, 6/16 +2 %: without the offload the MUFU binds, beyond 5/16 the issue slots do (a polynomial pair costs 14
 // instructions against 4 for a MUFU pair).
+// The decoder shape (d = 48: 3 + 3 MMAs per block instead of 4 + 4, so the softmax weighs more) prefers 5/16 (0.633 vs 0.649 ms).
 #ifndef ATT_POLY_MASK
-#define ATT_POLY_MASK 0x1248
+#define ATT_POLY_MASK(DV) ((DV) == 48 ? 0x4924 : 0x1248)
 #endif
 #ifndef ATT_REGS_SOFTMAX
 #define ATT_REGS_SOFTMAX 96                             // setmaxnreg budgets (multiples of 8): 8*96 + 4*40 <= 12*80
@@ -133,12 +134,29 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const AttnParams& p) 
   return t;
 }
 
-// 2^x for a pair on the FMA / ALU pipes, clamped to [-126, 128]: below it flushes towards 0, at 128 the exponent
-// field saturates to inf / NaN, which the row-sum range check catches (see exp2_poly2 for the polynomial)
+// 2^x for a pair on the FMA / ALU pipes.  x is clamped to [-125, 125] with ONE instruction per element
+// (min.xorsign.abs -> FMNMX.XORSIGN: sign(x) * min(|x|, 125)): below, the result is ~2^-125 (nothing next to row sums
+// >= 2^-80); above, it is ~2^125, which pushes the row sum past ATT_L_MAX so the tile is redone -- an unclamped exponent
+// insert would wrap into the sign bit and go unnoticed.  Round-to-nearest split x = n + r with the 1.5 * 2^23 magic
+// constant, cubic minimax polynomial for 2^r on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P).
+__device__ __forceinline__ float clamp_sym125(float x) {
+  float d;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(x), "f"(125.0f));
+  return d;
+}
 __device__ __forceinline__ float2 exp2_poly2_clamped(float2 x) {
-  x.x = fminf(x.x, 128.0f);
-  x.y = fminf(x.y, 128.0f);
-  return exp2_poly2(x);
+  x.x = clamp_sym125(x.x);
+  x.y = clamp_sym125(x.y);
+  const float2 t = fadd2(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 nf = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = ffma2(nf, make_float2(-1.0f, -1.0f), x);
+  float2 p = ffma2(make_float2(0.055171460f, 0.055171460f), r, make_float2(0.24261086f, 0.24261086f));
+  p = ffma2(p, r, make_float2(0.69326097f, 0.69326097f));
+  p = ffma2(p, r, make_float2(0.99992812f, 0.99992812f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  y.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return y;
 }
 
 template <int DQK_STEPS, int DV, bool SCALE1>
@@ -404,7 +422,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             float2 a;
             if (ATT_DBG & 2) {
               a = x;
-            } else if (!MASK && ((ATT_POLY_MASK >> i) & 1)) {
+            } else if (!MASK && ((ATT_POLY_MASK(DV) >> i) & 1)) {
               a = exp2_poly2_clamped(x);
             } else {
               a.x = fast_exp2(x.x);

@@ -232,6 +232,8 @@ class Engine:
         # ms: the second pass over the row block costs what the LayerNorm kernel did), so the proven plan stays default.
         self.fuse_ln = self.fuse_residual and os.environ.get("XS_FUSE_LN", "0") == "1"
         self.prof = None  # list of (tag, algorithmic flops, algorithmic bytes, start event, stop event) when profiling
+        self._last_stream = None   # the engine's scratch buffers are shared by every call: see serialise()
+        self._last_event = None
 
     @contextmanager
     def _op(self, tag, flops=0.0, nbytes=0.0, launches=1):
@@ -524,10 +526,32 @@ class Engine:
             call("xs_lse_merge_peers", ptrs_dev, base, B * P * C, _ptr(att), _ptr(lse_out), n_parts, B, P, DEC_HEADS,
                  DEC_D, DT_F32, st)
 
+    @contextmanager
+    def serialise(self):
+        """The scratch buffers (h, y, qkv, ...) belong to the engine, not to a call, so two calls on DIFFERENT streams
+        must not overlap on the device.  A call made on another stream than the previous one first waits for that one's
+        completion event; calls on one stream (the normal case, and every CUDA-graph capture) cost nothing extra."""
+        cur = torch.cuda.current_stream(self.device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing and self._last_event is not None and self._last_stream != cur.cuda_stream:
+            cur.wait_event(self._last_event)
+        try:
+            yield
+        finally:
+            if not capturing:
+                if self._last_event is None or self._last_stream != cur.cuda_stream:
+                    self._last_event = torch.cuda.Event()
+                self._last_event.record(cur)
+                self._last_stream = cur.cuda_stream
+
     # ---- the reference-shaped forward ------------------------------------------------------------
     def forward(self, query_img, ref_imgs, need_attn_weights=False, head_id=0):
         if need_attn_weights and not 0 <= head_id < DEC_HEADS:
             raise IndexError(f"need_attn_weights_head_id={head_id} out of range for {DEC_HEADS} heads")
+        with self.serialise():
+            return self._forward(query_img, ref_imgs, need_attn_weights, head_id)
+
+    def _forward(self, query_img, ref_imgs, need_attn_weights, head_id):
         st = torch.cuda.current_stream(self.device).cuda_stream
         B, _, H, Wd = query_img.shape
         N = ref_imgs.shape[1]

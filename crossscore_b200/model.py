@@ -146,9 +146,10 @@ class CrossScoreNet(nn.Module):
         P = (H // 14) * (W // 14)
         refs = None if ref_cross_imgs is None else ref_cross_imgs.contiguous()
         zero_pe = torch.zeros(P, 384, device=query_img.device)  # same kernels, PE table of zeros
-        xq32, mem = eng.features(query_img.contiguous(), refs, st, pe_table=zero_pe)
-        return {"query": xq32.view(B, P, 384).clone(),
-                "ref_cross": None if mem is None else mem.float().view(B, -1, 384).clone()}
+        with eng.serialise():
+            xq32, mem = eng.features(query_img.contiguous(), refs, st, pe_table=zero_pe)
+            return {"query": xq32.view(B, P, 384).clone(),
+                    "ref_cross": None if mem is None else mem.float().view(B, -1, 384).clone()}
 
     @staticmethod
     def _check_inputs(query_img, ref_cross_imgs):

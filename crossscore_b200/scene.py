@@ -52,6 +52,14 @@ def _dist_info(group):
     return 1, 0
 
 
+def _serialised(engine):
+    """Engine.serialise() (scratch buffers are per engine: calls on different streams are ordered); engines without it
+    (the CPU fakes of the host-logic tests) need nothing."""
+    import contextlib
+    fn = getattr(engine, "serialise", None)
+    return fn() if fn is not None else contextlib.nullcontext()
+
+
 def _stream(device):
     if torch.device(device).type == "cuda":
         return torch.cuda.current_stream(device).cuda_stream
@@ -89,8 +97,9 @@ class SceneScorer:
         kv = torch.empty(N * P, eng.kv_width, device=self.device, dtype=getattr(eng, "kv_dtype", eng.adtype))
         lo, hi = shard_range(N, self.world, self.rank)
         if hi > lo:
-            _, mem = eng.features(None, ref_imgs[lo:hi].contiguous(), st)
-            eng.project_kv(mem, st, out=kv[lo * P:hi * P])
+            with _serialised(eng):
+                _, mem = eng.features(None, ref_imgs[lo:hi].contiguous(), st)
+                eng.project_kv(mem, st, out=kv[lo * P:hi * P])
         self.cache_bytes_received = 0
         if self.world > 1:
             for owner in range(self.world):
@@ -127,8 +136,9 @@ class SceneScorer:
         ph, pw = H // PATCH, W // PATCH
         P = ph * pw
         eng, st = self.engine, _stream(self.device)
-        xq32, _ = eng.features(query_imgs, None, st)
-        score, _ = eng.decode(xq32, self.kv, Bq, P, self.n_ref * P, ph, pw, st, kv_shared=True)
+        with _serialised(eng):
+            xq32, _ = eng.features(query_imgs, None, st)
+            score, _ = eng.decode(xq32, self.kv, Bq, P, self.n_ref * P, ph, pw, st, kv_shared=True)
         return score
 
     def _score_graphed(self, query_imgs: torch.Tensor) -> torch.Tensor:

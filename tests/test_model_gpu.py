@@ -165,6 +165,30 @@ def test_in_place_weight_edit_is_seen():
     assert (b - d).abs().max().item() < 1e-5 and (c - d).abs().max().item() > 1e-2
 
 
+def test_calls_on_different_streams_are_serialised():
+    """the engine's scratch buffers are per engine, not per call.  Forwards issued back to back on two streams
+    (and a get_featmaps in between) must give the same maps as on one stream."""
+    rec = load_golden("g7_168x154_n1")
+    net, q, r = build_net(rec, "bf16")
+    q2, r2 = make_inputs(1, 1, 168, 154, seed=77)
+    q2, r2 = q2.to(DEV), r2.to(DEV)
+    want1 = net(q, r, False, 0, False)["score_map_ref_cross"].clone()
+    want2 = net(q2, r2, False, 0, False)["score_map_ref_cross"].clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            a = net(q, r, False, 0, False)["score_map_ref_cross"]
+        with torch.cuda.stream(s2):
+            net.get_featmaps(q2, r2)
+            b = net(q2, r2, False, 0, False)["score_map_ref_cross"]
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a, want1) and torch.equal(b, want2)
+
+
 def test_get_featmaps_does_not_touch_forward_tables():
     """get_featmaps passes its zero PE table as an argument (it used to swap it into the engine's shared cache)."""
     rec = load_golden("g2_nonsquare_84x117_n3_attn")
