@@ -36,6 +36,7 @@ SIGNATURES = {
     "xs_gemm_bias_residual_ln": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _p, _f, _p, _i, _i, _i, _i, _i, _p]),
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_attn_set_optimistic": (None, [_i]),
+    "xs_attn_set_layout": (None, [_i]),
     "xs_lse_merge": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _i, _p]),
     "xs_head_score_jigsaw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
     "xs_lse_merge_peers": (_i, [_p, _ll, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

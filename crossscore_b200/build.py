@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcrossscore_sm100a.so")
-SOURCES = ["xs_api.cu", "xs_gemm_tc.cu", "xs_attn_tc.cu", "xs_rows.cu", "xs_f32.cu", "xs_imgproc.cu"]
+SOURCES = ["xs_api.cu", "xs_gemm_tc.cu", "xs_attn_tc.cu", "xs_attn_tc2.cu", "xs_rows.cu", "xs_f32.cu", "xs_imgproc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

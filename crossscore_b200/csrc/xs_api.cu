@@ -86,6 +86,7 @@ int head_jigsaw_tc(const void*, int, const void*, int, const float*, float*, int
 int flash_attn_bf16_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long,
                        long long, long long, long long, int, int, int, float, cudaStream_t);
 void attn_set_optimistic(int);
+void attn_set_layout(int);
 int gemm_f32(const float*, int, const float*, int, const float*, float*, int, int, int, int, int, cudaStream_t);
 int preprocess_u8(const uint8_t*, int, int, int, float*, int, int, const float*, cudaStream_t);
 size_t postprocess_workspace_bytes(int);
@@ -254,6 +255,7 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
 }
 
 void xs_attn_set_optimistic(int enable) { attn_set_optimistic(enable); }
+void xs_attn_set_layout(int layout) { attn_set_layout(layout); }
 
 int xs_lse_merge(const float* o_parts, const float* lse_parts, void* out, float* lse_out, int n_parts, int B, int Lq,
                  int heads, int head_dim, long long o_part_stride, long long lse_part_stride, int dtype,

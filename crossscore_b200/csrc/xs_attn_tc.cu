@@ -592,6 +592,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // xs_attn_set_optimistic(0) forces every tile through the online-softmax pass (tests exercise it on benign inputs)
 static std::atomic<int> g_attn_optimistic{1};
 void attn_set_optimistic(int enable) { g_attn_optimistic.store(enable ? 1 : 0); }
+int attn_optimistic_enabled() { return g_attn_optimistic.load(); }
+// 0: this kernel (64-key blocks, two CTAs per SM); 1: the pair kernel of xs_attn_tc2.cu where it applies
+static std::atomic<int> g_attn_layout{0};
+void attn_set_layout(int layout) { g_attn_layout.store(layout); }
+int flash_attn_bf16_pair(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long, long long,
+                         long long, long long, int, int, int, float, cudaStream_t);
 
 template <int DQK, int DV, bool SCALE1>
 static int launch_attn(dim3 grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
@@ -637,6 +643,11 @@ int flash_attn_bf16_tc(const void* q, const void* k, const void* v, void* o, flo
                    (kv_batch_stride % 8) == 0,
                "flash_attn: strides must be multiples of 8 elements");
   XS_CHECK_ARG(nsplit == 1 || (o_is_f32 && lse != nullptr), "flash_attn: split-KV needs fp32 partial O and LSE");
+  if (g_attn_layout.load() == 1) {
+    const int rc = flash_attn_bf16_pair(q, k, v, o, lse, B, heads, Lq, Lk, head_dim, q_row_stride, q_batch_stride,
+                                        kv_row_stride, kv_batch_stride, kv_shared, nsplit, o_is_f32, scale, stream);
+    if (rc != 1) return rc;
+  }
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t box[3] = {64, 128, 1};
   const uint32_t box_kv[3] = {64, ATT_BKV, 1};

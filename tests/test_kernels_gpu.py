@@ -189,6 +189,15 @@ def test_gemm_bf16_rejects_bad_shapes():
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
+@pytest.fixture(params=[0, 1], ids=["layout64", "layout_pair"])
+def layout(request):
+    """Both bf16 flash-attention layouts: 64-key blocks with two CTAs per SM (xs_attn_tc.cu) and two query tiles per
+    CTA sharing 128-key blocks (xs_attn_tc2.cu)."""
+    _lib.load().xs_attn_set_layout(request.param)
+    yield request.param
+    _lib.load().xs_attn_set_layout(0)
+
+
 def attn_ref(q, k, v, scale):
     # q (B,H,Lq,d), k/v (B,H,Lk,d) double
     s = (q @ k.transpose(-1, -2)) * scale
@@ -249,8 +258,10 @@ def test_flash_attn_f32(B, H, Lq, Lk, d, slot, nsplit, shared):
     (1, 8, 300, 6845, 48, 1, False, 3.0),    # cross-attention, long kv, peaky softmax (lazy rescale path)
     (1, 8, 300, 6845, 48, 4, False, 1.0),    # split-KV + merge
     (3, 8, 200, 700, 48, 1, True, 1.0),      # shared reference K/V
+    (2, 3, 1370, 700, 64, 1, False, 1.0),    # odd tile count AND odd head count (pair layout: mixed units, a lone tile)
+    (2, 5, 300, 900, 48, 2, False, 1.0),     # the same with split-KV
 ])
-def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale):
+def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale, layout):
     o, ref, lse, lse_ref = run_attn(DT_BF16, B, H, Lq, Lk, d, 64, nsplit, shared, qscale=qscale)
     assert torch.isfinite(o).all()
     err = (o - ref).abs()
@@ -265,8 +276,9 @@ def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale):
     (1, 8, 300, 6845, 48, 1, False, 3.0),
     (1, 8, 300, 6845, 48, 4, False, 1.0),
     (3, 8, 200, 700, 48, 1, True, 1.0),
+    (2, 3, 1370, 700, 64, 1, False, 1.0),
 ])
-def test_flash_attn_bf16_tc_online_pass(B, H, Lq, Lk, d, nsplit, shared, qscale):
+def test_flash_attn_bf16_tc_online_pass(B, H, Lq, Lk, d, nsplit, shared, qscale, layout):
     """xs_attn_set_optimistic(0): every tile goes through the second (online softmax, per-block row max, O rescale)
     pass -- the path that otherwise only runs for tiles whose row sums left the safe range."""
     _lib.load().xs_attn_set_optimistic(0)
@@ -318,7 +330,7 @@ def _ramp_inputs(B, H, Lq, Lk, d, key_logit, seed=0):
 @pytest.mark.parametrize("d", [64, 48])
 @pytest.mark.parametrize("case", ["rising_small", "rising_large", "late_spike", "early_spike", "all_large",
                                   "all_very_negative", "falling_large"])
-def test_flash_attn_bf16_tc_adversarial_max(case, d):
+def test_flash_attn_bf16_tc_adversarial_max(case, d, layout):
     """The softmax reference point.  The first pass takes 2^logit with no maximum at all; rows whose sums leave
     [2^-80, 2^100] must be caught and redone with the online softmax: a row maximum that rises in every one of >= 100
     key blocks, a +30 spike in the last block, logits that are all huge or all hugely negative."""
@@ -342,7 +354,7 @@ def test_flash_attn_bf16_tc_adversarial_max(case, d):
     assert (lse - lse_ref).abs().max() < 0.05, case
 
 
-def test_flash_attn_bf16_tc_long_kv_rows_mixed():
+def test_flash_attn_bf16_tc_long_kv_rows_mixed(layout):
     """Lk = 87 616 (cfg 4 / cfg 5 key count), split and unsplit; half of the query rows see a rising maximum that
     overflows the optimistic pass, the other half stay benign, so redone and first-pass tiles mix in one launch."""
     Lq, Lk, d, H = 256, 87616, 48, 8
@@ -377,7 +389,7 @@ def test_gemm_f16_out():
 
 
 @pytest.mark.parametrize("nsplit", [1, 2])
-def test_flash_attn_bf16_tc_f32_out(nsplit):
+def test_flash_attn_bf16_tc_f32_out(nsplit, layout):
     """decoder configuration: bf16 q/k/v, fp32 attention output (feeds the TF32 out-proj GEMM)"""
     o, ref, lse, lse_ref = run_attn(DT_BF16, 2, 8, 300, 1400, 48, 64, nsplit, False, force_f32_out=True)
     err = (o - ref).abs()
