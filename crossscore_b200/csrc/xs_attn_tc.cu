@@ -594,7 +594,7 @@ static std::atomic<int> g_attn_optimistic{1};
 void attn_set_optimistic(int enable) { g_attn_optimistic.store(enable ? 1 : 0); }
 int attn_optimistic_enabled() { return g_attn_optimistic.load(); }
 // 0: this kernel (64-key blocks, two CTAs per SM); 1: the pair kernel of xs_attn_tc2.cu where it applies
-static std::atomic<int> g_attn_layout{0};
+static std::atomic<int> g_attn_layout{1};  // 1: pair kernel (xs_attn_tc2.cu), the default; 0: this file's kernel
 void attn_set_layout(int layout) { g_attn_layout.store(layout); }
 int flash_attn_bf16_pair(const void*, const void*, const void*, void*, float*, int, int, int, int, int, long long, long long,
                          long long, long long, int, int, int, float, cudaStream_t);

@@ -29,7 +29,10 @@ namespace xs {
 
 constexpr int AT2_THREADS = 640;
 constexpr int AT2_BKV = 128;                              // keys per block
-constexpr int AT2_ST = 4;                                 // K/V ring depth
+#ifndef AT2_STAGES
+#define AT2_STAGES 5
+#endif
+constexpr int AT2_ST = AT2_STAGES;                        // K/V ring depth
 #ifndef AT2_POLY_MASK
 #define AT2_POLY_MASK(DV) ((DV) == 48 ? 0x4924 : 0x4924)  // per 32-logit half: pairs on the FMA-pipe polynomial
 #endif

@@ -44,22 +44,47 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def attn_kv_splits(tiles: int, nblk: int, slots: int = 2 * NUM_SMS_HINT, max_splits: int = 8) -> int:
+ATTN_LAYOUT = 1  # the library's default kernel layout (xs_attn_set_layout): 1 = pair kernel, 0 = 64-key kernel
+
+
+def set_attn_layout(layout: int) -> None:
+    """Select the flash-attention kernel layout for the process (library switch + the key-split model below)."""
+    global ATTN_LAYOUT
+    if layout not in (0, 1):
+        raise ValueError("attention layout must be 0 or 1")
+    _lib.load().xs_attn_set_layout(int(layout))
+    ATTN_LAYOUT = int(layout)
+
+
+def attn_units(B: int, heads: int, Lq: int, layout: int = None):
+    """(work units of one key range, persistent CTA slots, microseconds per 128-key block and unit) of a launch.
+
+    Layout 1 (xs_attn_tc2.cu): one CTA per SM walks pairs of 128-row query tiles -- per (batch): heads * (tiles // 2) pairs
+    plus, for an odd tile count, ceil(heads / 2) units made of the last tiles of two heads.  Layout 0 (xs_attn_tc.cu):
+    two CTAs per SM, one 128-row tile each.  Block times measured stand-alone on cfg 2's DINOv2 shape (r2t)."""
+    layout = ATTN_LAYOUT if layout is None else layout
+    nq = (Lq + 127) // 128
+    if layout == 1:
+        return B * (heads * (nq // 2) + ((heads + 1) // 2 if nq & 1 else 0)), NUM_SMS_HINT, 1.4
+    return B * heads * nq, 2 * NUM_SMS_HINT, 1.45
+
+
+def attn_kv_splits(units: int, nblk: int, slots: int = NUM_SMS_HINT, t_blk: float = 1.4, max_splits: int = 8) -> int:
     """How many key ranges a flash-attention launch is cut into (partials merged by xs_lse_merge).
 
-    The kernel is persistent with `slots` CTAs (two per SM) walking `tiles * nsplit` equally long tiles, so a launch takes
-    ceil(tiles * nsplit / slots) waves of (tile time / nsplit).  Few tiles (a single query: 8 heads x 11 query tiles = 88)
-    leave most SMs idle, and a tile count just above a multiple of `slots` (cfg 5's cross-attention: 344 tiles on 296
-    slots) pays a nearly empty second wave -- both are fixed by splitting the keys.  A split costs an fp32 partial-output
-    round trip and the merge launch (~15 us, measured), so short launches (the DINOv2 attention of a handful of images:
-    8 us per tile) are left alone.  Tile time: ~0.8 us per 128 keys (measured: 570 clk per 64-key block at ~1.5 GHz)."""
-    t_tile = 0.8 * nblk  # microseconds
+    The kernel is persistent with `slots` CTAs walking `units * nsplit` equally long work units (attn_units), so a launch
+    takes ceil(units * nsplit / slots) waves of (unit time / nsplit).  Few units (a single query: 8 heads x 11 query
+    tiles = 44 pair units) leave most SMs idle, and a unit count just above a multiple of `slots` pays a nearly empty last
+    wave -- both are fixed by splitting the keys.  A split costs an fp32 partial-output round trip and the merge launch
+    (~15 us, measured), so short launches (the DINOv2 attention of a handful of images: ~15 us per unit) are left
+    alone.  `t_blk`: microseconds per 128-key block of one unit."""
+    t_unit = t_blk * nblk  # microseconds
     best, best_t = 1, None
     for n in range(1, max(1, min(max_splits, nblk // 4)) + 1):
         per = -(-nblk // n)
         if -(-nblk // per) != n:  # every split must own at least one key block
             continue
-        t = -(-tiles * n // slots) * t_tile / n + (15.0 if n > 1 else 0.0)
+        t = -(-units * n // slots) * t_unit / n + (15.0 if n > 1 else 0.0)
         if best_t is None or t < best_t * 0.97:  # prefer fewer splits on near-ties
             best, best_t = n, t
     return best
@@ -315,7 +340,8 @@ class Engine:
         """q/k/v are tensor views whose data_ptr is the first column of the respective part; o is bf16 or
         fp32 (B*Lq, heads*d)."""
         scale = self.attn_scale(d)
-        nsplit = attn_kv_splits(B * heads * ((Lq + 127) // 128), (Lk + 127) // 128)
+        units, slots, t_blk = attn_units(B, heads, Lq)
+        nsplit = attn_kv_splits(units, (Lk + 127) // 128, slots, t_blk)
         o_is_f32 = 1 if o.dtype == torch.float32 else 0
         flops = 4.0 * B * heads * Lq * Lk * d  # QK^T + PV
         if nsplit == 1:

@@ -103,12 +103,17 @@ def test_product_never_imports_oracle():
 
 def test_attention_key_split_heuristic():
     """Engine picks the number of key ranges from the wave efficiency of the persistent attention kernel."""
-    from crossscore_b200.engine import attn_kv_splits
-    assert attn_kv_splits(192 * 6 * 11, 11) == 1        # cfg 2 DINOv2 attention: 42.8 waves, nothing to gain
-    assert attn_kv_splits(32 * 8 * 11, 54) == 1         # cfg 2 cross-attention
-    assert attn_kv_splits(88, 685) == 3                 # one query: 88 tiles -> 264 on 296 slots
-    assert attn_kv_splits(8 * 43, 685) == 5             # cfg 5 cross-attention: 344 tiles = 1.16 waves -> 5.8 waves
-    assert attn_kv_splits(88, 3) == 1                   # too few key blocks to split
+    from crossscore_b200.engine import attn_kv_splits, attn_units
+    # layout 1 (pair kernel, 148 slots): units per batch = heads * (tiles // 2) + ceil(heads / 2) for an odd tile count
+    assert attn_units(192, 6, 1370, 1) == (192 * 33, 148, 1.4)
+    assert attn_units(1, 8, 1369, 1)[0] == 44 and attn_units(1, 5, 300, 1)[0] == 8 and attn_units(2, 8, 256, 1)[0] == 16
+    assert attn_units(192, 6, 1370, 0) == (192 * 66, 296, 1.45)
+    assert attn_kv_splits(192 * 33, 11) == 1             # cfg 2 DINOv2 attention: 42.8 waves, nothing to gain
+    assert attn_kv_splits(32 * 44, 54) == 1              # cfg 2 cross-attention
+    assert attn_kv_splits(44, 685) == 3                  # one query: 44 units -> 132 on 148 slots
+    assert attn_kv_splits(8 * 22, 685) == 5              # cfg 5 cross-attention: 176 units = 1.19 waves -> 5.9 waves
+    assert attn_kv_splits(44, 3) == 1                    # too few key blocks to split
+    assert attn_kv_splits(88, 685, 296, 1.45) == 3       # the same single query in layout 0
     for tiles, nblk in [(1, 1), (7, 9), (300, 40), (5000, 2)]:
         n = attn_kv_splits(tiles, nblk)
         per = -(-nblk // n)
