@@ -37,6 +37,13 @@ constexpr int AT2_ST = AT2_STAGES;                        // K/V ring depth
 #define AT2_POLY_MASK(DV) ((DV) == 48 ? 0x4924 : 0x4924)  // per 32-logit half: pairs on the FMA-pipe polynomial
 #endif
 constexpr int AT2_MAX_UNITS_PER_CTA = 1024;
+// Launched at 96 registers per thread; setmaxnreg then moves registers from the control warpgroup to the 16 softmax warps
+// inside the CTA's own pool of 640 x 96 = 61 440: 512 x 104 + 128 x 64 = 61 440 (112 / 32 spills in the control warps).
+#ifndef AT2_REGS_SOFTMAX
+#define AT2_REGS_SOFTMAX 104
+#define AT2_REGS_CTRL 64
+#endif
+static_assert(512 * AT2_REGS_SOFTMAX + 128 * AT2_REGS_CTRL <= 640 * 96, "setmaxnreg budget exceeds the CTA's register pool");
 constexpr float AT2_L_MIN = 8.2718061e-25f;               // 2^-80
 constexpr float AT2_L_MAX = 1.2676506e30f;                // 2^100
 constexpr uint32_t AT2_Q_BYTES = 128 * 64 * 2;            // 16 KB per query tile
@@ -66,9 +73,12 @@ struct Attn2Params {
 // the time).  A mixed unit's second tile is absent when the head count is odd.
 struct Unit {
   int b, split, kv_begin, kv_end, nkb;
-  int q0[2], h[2];
-  bool valid[2];
+  int q0a, q0b, ha, hb;  // per tile (scalars: a runtime-indexed array would live in local memory)
+  bool valid_b;          // tile A is always present
   bool shared;
+  __device__ __forceinline__ int q0(int tt) const { return tt ? q0b : q0a; }
+  __device__ __forceinline__ int h(int tt) const { return tt ? hb : ha; }
+  __device__ __forceinline__ bool valid(int tt) const { return tt ? valid_b : true; }
 };
 __device__ __forceinline__ Unit decode_unit(int u, const Attn2Params& p) {
   Unit t;
@@ -80,19 +90,18 @@ __device__ __forceinline__ Unit decode_unit(int u, const Attn2Params& p) {
   const int n_shared = p.heads * p.n_pairs_full;
   if (loc < n_shared) {
     const int pr = loc % p.n_pairs_full;
-    t.h[0] = t.h[1] = loc / p.n_pairs_full;
-    t.q0[0] = pr * 256;
-    t.q0[1] = pr * 256 + 128;
-    t.valid[0] = t.valid[1] = true;
+    t.ha = t.hb = loc / p.n_pairs_full;
+    t.q0a = pr * 256;
+    t.q0b = pr * 256 + 128;
+    t.valid_b = true;
     t.shared = true;
   } else {
     const int m = loc - n_shared;
-    t.h[0] = 2 * m;
-    t.h[1] = 2 * m + 1;
-    t.q0[0] = t.q0[1] = p.n_pairs_full * 256;  // the odd last tile of each head
-    t.valid[0] = true;
-    t.valid[1] = t.h[1] < p.heads;
-    if (!t.valid[1]) t.h[1] = t.h[0];
+    t.ha = 2 * m;
+    t.hb = 2 * m + 1;
+    t.q0a = t.q0b = p.n_pairs_full * 256;  // the odd last tile of each head
+    t.valid_b = t.hb < p.heads;
+    if (!t.valid_b) t.hb = t.ha;
     t.shared = false;
   }
   t.kv_begin = t.split * p.split_len;
@@ -188,6 +197,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     return pass == 0 || ((redo[idx >> 5] >> (idx & 31)) & 1u) != 0u;
   };
 
+  if (warp >= 16) reg_dealloc<AT2_REGS_CTRL>();
   if (warp == 16) {
     // ===================== TMA producer =====================
     uint32_t g = 0;          // 128-key blocks over the CTA's lifetime
@@ -198,12 +208,13 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (!selected(pass, idx)) continue;
         const Unit t = decode_unit(u, p);
         const int b_kv = p.kv_shared ? 0 : t.b;
+#pragma unroll
         for (int tt = 0; tt < 2; ++tt) {
-          if (!t.valid[tt]) continue;
+          if (!t.valid(tt)) continue;
           mbar_wait(q_empty + tt, (nu[tt] & 1) ^ 1);  // previous unit's QK^T are done with this Q buffer
           if (elect_one_sync()) {
             mbar_expect_tx(q_full + tt, AT2_Q_BYTES);
-            tma_load_3d(smQ + tt * AT2_Q_BYTES, &tmQ, q_full + tt, t.h[tt] * 64, t.q0[tt], t.b);
+            tma_load_3d(smQ + tt * AT2_Q_BYTES, &tmQ, q_full + tt, t.h(tt) * 64, t.q0(tt), t.b);
           }
           __syncwarp();
           ++nu[tt];
@@ -212,12 +223,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int j = 0; j < t.nkb; ++j) {
           const int kv0 = t.kv_begin + j * AT2_BKV;
           for (int tt = 0; tt < 2; ++tt) {  // shared: one stage for both tiles; mixed: one stage per tile
-            if (!t.valid[tt] || (t.shared && tt == 1)) continue;
+            if (!t.valid(tt) || (t.shared && tt == 1)) continue;
             mbar_wait(kv_empty + s, ph ^ 1);
             if (elect_one_sync()) {
               mbar_expect_tx(kv_full + s, 2 * AT2_KV_BYTES);
-              tma_load_3d(smK + s * AT2_KV_BYTES, &tmK, kv_full + s, t.h[tt] * 64, kv0, b_kv);
-              tma_load_3d(smV + s * AT2_KV_BYTES, &tmV, kv_full + s, t.h[tt] * 64, kv0, b_kv);
+              tma_load_3d(smK + s * AT2_KV_BYTES, &tmK, kv_full + s, t.h(tt) * 64, kv0, b_kv);
+              tma_load_3d(smV + s * AT2_KV_BYTES, &tmV, kv_full + s, t.h(tt) * 64, kv0, b_kv);
             }
             __syncwarp();
             ++g;
@@ -241,10 +252,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (!selected(pass, idx)) continue;
         const Unit t = decode_unit(u, p);
         uint32_t s = g % AT2_ST;
-        const int last_tt = t.valid[1] ? 1 : 0;
+        const int last_tt = t.valid_b ? 1 : 0;
         for (int j = 0; j < t.nkb; ++j) {
           for (int tt = 0; tt < 2; ++tt) {
-            if (!t.valid[tt]) continue;
+            if (!t.valid(tt)) continue;
             mbar_wait(p_full + tt, cb[tt] & 1);  // softmax has written P_t of this block
             if (j == 0) mbar_wait(o_empty + tt, (nu[tt] & 1) ^ 1);  // previous unit's O_t has been read out
             tc_fence_after();
@@ -270,7 +281,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         ++nu[0];
-        if (t.valid[1]) ++nu[1];
+        if (t.valid_b) ++nu[1];
       }
       if (pass == 0) named_bar_sync(1, AT2_THREADS);
     }
@@ -289,10 +300,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (!selected(pass, idx)) continue;
         const Unit t = decode_unit(u, p);
         uint32_t s = g % AT2_ST, ph = (g / AT2_ST) & 1;
-        const int last_tt = t.valid[1] ? 1 : 0;
+        const int last_tt = t.valid_b ? 1 : 0;
         for (int j = 0; j < t.nkb; ++j) {
           for (int tt = 0; tt < 2; ++tt) {
-            if (!t.valid[tt]) continue;
+            if (!t.valid(tt)) continue;
             if (!t.shared || tt == 0) mbar_wait(kv_full + s, ph);  // K (and V) of this stage have landed
             if (j == 0) mbar_wait(q_full + tt, nu[tt] & 1);
             mbar_wait(s_free + tt, (cb[tt] & 1) ^ 1);  // the previous block's S_t has been read into registers
@@ -315,7 +326,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         ++nu[0];
-        if (t.valid[1]) ++nu[1];
+        if (t.valid_b) ++nu[1];
       }
       if (pass == 0) named_bar_sync(1, AT2_THREADS);
     }
@@ -323,6 +334,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     named_bar_sync(1, AT2_THREADS);
   } else {
     // ===================== softmax / epilogue: tile tt = warp / 8, 16 rows per warp ==========
+    reg_alloc<AT2_REGS_SOFTMAX>();
     const int tt = warp >> 3;
     const int w8 = warp & 7;
     const int lane_base = (w8 & 3) * 32 + (w8 >> 2) * 16;
@@ -374,7 +386,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto unit_fn = [&](const int u, const int idx, auto safe_tag) {
       constexpr bool SAFE = decltype(safe_tag)::value;
       const Unit t = decode_unit(u, p);
-      if (!t.valid[tt]) return;
+      if (!t.valid(tt)) return;
       const int nkb = t.nkb;
       const int tail_valid = t.kv_end - t.kv_begin - (nkb - 1) * AT2_BKV;  // valid columns of the last block (1..128)
       float mA = -INFINITY, mB = -INFINITY;
@@ -429,22 +441,41 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           nmA = -mA;
           nmB = -mB;
         }
-        // ---- first half: columns [0, 64) ----
-        tmem_ld_16x256b_x8(t_s, v);
-        tmem_ld_wait32(v);
-        if constexpr (MASK) mask_half(v, tail_valid);
-        exp_half(v, pk, lA, lB, nmA, nmB, safe_tag, mask_tag);
-        if constexpr (!SAFE) mbar_wait(p_free + tt, (cb & 1) ^ 1);  // PV of the previous block has read P_t
-        tmem_st_16x128b_x8(t_p, pk);
-        // ---- second half: columns [64, 128); S_t is free once it is in registers ----
-        tmem_ld_16x256b_x8(t_s + 64, v);
-        tmem_ld_wait32(v);
-        tc_fence_before();
-        __syncwarp();
-        if (elect_one_sync()) mbar_arrive(s_free + tt);
-        if constexpr (MASK) mask_half(v, tail_valid - 64);
-        exp_half(v, pk, lA, lB, nmA, nmB, safe_tag, mask_tag);
-        tmem_st_16x128b_x8(t_p + 32, pk);
+        if constexpr (SAFE) {
+          // ---- first half: columns [0, 64) ----
+          tmem_ld_16x256b_x8(t_s, v);
+          tmem_ld_wait32(v);
+          if constexpr (MASK) mask_half(v, tail_valid);
+          exp_half(v, pk, lA, lB, nmA, nmB, safe_tag, mask_tag);
+          tmem_st_16x128b_x8(t_p, pk);
+          // ---- second half: columns [64, 128); S_t is free once it is in registers ----
+          tmem_ld_16x256b_x8(t_s + 64, v);
+          tmem_ld_wait32(v);
+          tc_fence_before();
+          __syncwarp();
+          if (elect_one_sync()) mbar_arrive(s_free + tt);
+          if constexpr (MASK) mask_half(v, tail_valid - 64);
+          exp_half(v, pk, lA, lB, nmA, nmB, safe_tag, mask_tag);
+          tmem_st_16x128b_x8(t_p + 32, pk);
+        } else {
+          // Both halves of S_t go to registers first and S_t is released at once: QK^T of the next block then runs
+          // under ALL of this block's exponentials, and no tcgen05.ld latency sits between the two halves.
+          uint32_t v1[32];
+          tmem_ld_16x256b_x8(t_s, v);
+          tmem_ld_16x256b_x8(t_s + 64, v1);
+          tmem_ld_wait32(v);
+          tmem_ld_wait32(v1);
+          tc_fence_before();
+          __syncwarp();
+          if (elect_one_sync()) mbar_arrive(s_free + tt);
+          if constexpr (MASK) mask_half(v, tail_valid);
+          exp_half(v, pk, lA, lB, nmA, nmB, safe_tag, mask_tag);
+          mbar_wait(p_free + tt, (cb & 1) ^ 1);  // PV of the previous block has read P_t
+          tmem_st_16x128b_x8(t_p, pk);
+          if constexpr (MASK) mask_half(v1, tail_valid - 64);
+          exp_half(v1, pk, lA, lB, nmA, nmB, safe_tag, mask_tag);
+          tmem_st_16x128b_x8(t_p + 32, pk);
+        }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -484,9 +515,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       const float invA = 1.0f / la, invB = 1.0f / lb;
-      const int rowA = t.q0[tt] + rA, rowB = rowA + 8;
+      const int rowA = t.q0(tt) + rA, rowB = rowA + 8;
       const long long base = static_cast<long long>(t.split) * p.o_split_stride +
-                             static_cast<long long>(t.b) * p.o_batch_stride + static_cast<long long>(t.h[tt]) * DV + cq;
+                             static_cast<long long>(t.b) * p.o_batch_stride + static_cast<long long>(t.h(tt)) * DV + cq;
       const long long offA = base + static_cast<long long>(rowA) * p.o_row_stride;
       const long long offB = base + static_cast<long long>(rowB) * p.o_row_stride;
       if (p.o_is_f32) {
@@ -514,7 +545,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       if (p.lse != nullptr && (lane & 3) == 0) {
         float* lse = p.lse + static_cast<long long>(t.split) * p.lse_split_stride +
-                     (static_cast<long long>(t.b) * p.heads + t.h[tt]) * p.Lq;
+                     (static_cast<long long>(t.b) * p.heads + t.h(tt)) * p.Lq;
         const float m0A = SAFE ? mA : 0.f, m0B = SAFE ? mB : 0.f;
         if (rowA < p.Lq) lse[rowA] = (m0A + log2f(la)) * 0.6931471805599453f;
         if (rowB < p.Lq) lse[rowB] = (m0B + log2f(lb)) * 0.6931471805599453f;
