@@ -142,7 +142,7 @@ int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* l
  *     enable = 0 sends every tile through the online-softmax pass (process-wide; default 1). */
 void xs_attn_set_optimistic(int enable);
 /*     layout 0: 64-key blocks, two CTAs per SM (xs_attn_tc.cu); 1: two query tiles per CTA sharing 128-key K/V blocks
- *     (xs_attn_tc2.cu).  Process-wide; the results are the same up to summation order. */
+ *     (xs_attn_tc2.cu; the default).  Process-wide; the results are the same up to summation order. */
 void xs_attn_set_layout(int layout);
 
 /* C2  split-KV merge: LSE = log sum_r exp(LSE_r), O = sum_r exp(LSE_r - LSE) O_r  (no reference counterpart;

@@ -9,6 +9,19 @@ from crossscore_b200.synthetic import make_inputs, make_state_dict
 ALL = ["w", "img", "tok", "y", "qkv", "p", "att", "d", "g", "x", "dqkv", "dp", "datt", "dd", "df", "hf", "mem", "kv"]
 
 
+def ln_fold(h, gamma, beta, W, b, eps=1e-6):
+    """LayerNorm folded into the GEMM that follows: bf16(h) x bf16(gamma * W)^T in fp32, then per row
+    rstd * (acc - mean * c1) + (W beta + b); mean / rstd from the fp32 h."""
+    dt = h.dtype
+    mean = h.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(h.var(-1, unbiased=False, keepdim=True) + eps)
+    Wf = (W * gamma[None, :]).bfloat16().to(dt)
+    c1 = Wf.sum(-1)
+    c0 = W @ beta + b
+    acc = h.bfloat16().to(dt) @ Wf.T
+    return rstd * (acc - mean * c1) + c0
+
+
 def run(sd, q, r, active, dt=torch.float32):
     R = lambda x, tag: x.bfloat16().to(dt) if tag in active else x
     g = lambda k: sd[k].to(dt)
@@ -28,10 +41,13 @@ def run(sd, q, r, active, dt=torch.float32):
     for l in range(12):
         p = f"backbone.encoder.layer.{l}."
         lam1, lam2 = g(p + "layer_scale1.lambda1"), g(p + "layer_scale2.lambda1")
-        y = R(O.layer_norm(h, g(p + "norm1.weight"), g(p + "norm1.bias"), 1e-6), "y")
-        wqkv = R(torch.cat([g(p + f"attention.attention.{n}.weight") for n in ("query", "key", "value")], 0), "w")
+        wqkv0 = torch.cat([g(p + f"attention.attention.{n}.weight") for n in ("query", "key", "value")], 0)
         bqkv = torch.cat([g(p + f"attention.attention.{n}.bias") for n in ("query", "key", "value")], 0)
-        qkv = R(y @ wqkv.T + bqkv, "qkv")
+        if "fold" in active:
+            qkv = R(ln_fold(h, g(p + "norm1.weight"), g(p + "norm1.bias"), wqkv0, bqkv), "qkv")
+        else:
+            y = R(O.layer_norm(h, g(p + "norm1.weight"), g(p + "norm1.bias"), 1e-6), "y")
+            qkv = R(y @ R(wqkv0, "w").T + bqkv, "qkv")
         qq, kk, vv = [t.view(I, T, 6, 64).transpose(1, 2) for t in qkv.split(384, -1)]
         s = qq @ kk.transpose(-1, -2)
         if "s16" in active:  # fp16 logit accumulators (tcgen05 D format f16)
@@ -48,8 +64,11 @@ def run(sd, q, r, active, dt=torch.float32):
         a = R(a.transpose(1, 2).reshape(I, T, 384), "att")
         d = R(a @ R(g(p + "attention.output.dense.weight") * lam1[:, None], "w").T + g(p + "attention.output.dense.bias") * lam1, "d")
         h = h + d
-        y = R(O.layer_norm(h, g(p + "norm2.weight"), g(p + "norm2.bias"), 1e-6), "y")
-        m = R(O.gelu_erf(y @ gw(p + "mlp.fc1.weight").T + g(p + "mlp.fc1.bias")), "g")
+        if "fold" in active:
+            m = R(O.gelu_erf(ln_fold(h, g(p + "norm2.weight"), g(p + "norm2.bias"), g(p + "mlp.fc1.weight"), g(p + "mlp.fc1.bias"))), "g")
+        else:
+            y = R(O.layer_norm(h, g(p + "norm2.weight"), g(p + "norm2.bias"), 1e-6), "y")
+            m = R(O.gelu_erf(y @ gw(p + "mlp.fc1.weight").T + g(p + "mlp.fc1.bias")), "g")
         d = R(m @ R(g(p + "mlp.fc2.weight") * lam2[:, None], "w").T + g(p + "mlp.fc2.bias") * lam2, "d")
         h = h + d
     f = O.layer_norm(h, g("backbone.layernorm.weight"), g("backbone.layernorm.bias"), 1e-6)[:, 1:]
@@ -99,6 +118,15 @@ if __name__ == "__main__":
     def err(active):
         d = (run(sd, q, r, set(active)).double() - base).abs()
         return d.max().item(), d.mean().item()
+    if len(sys.argv) > 1 and sys.argv[1] == "fold":
+        for variant in ("benign", "outlier"):
+            sd = make_state_dict(1, variant=variant)
+            base = run(sd, q, r, set(), torch.float64)
+            print(variant, "all        ", err(ALL))
+            print(variant, "all + fold ", err(ALL + ["fold"]))
+            print(variant, "only y     ", err(["y", "w"]))
+            print(variant, "only fold  ", err(["fold", "w"]))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f16":
         print("all             ", err(ALL))
         print("all + s16       ", err(ALL + ["s16"]))
