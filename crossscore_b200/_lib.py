@@ -34,6 +34,9 @@ SIGNATURES = {
     "xs_gemm_bias_act": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "xs_gemm_bias_residual": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "xs_gemm_bias_residual_ln": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _p, _f, _p, _i, _i, _i, _i, _i, _p]),
+    "xs_gemm_bias_residual_stats": (_i, [_p, _i, _p, _i, _p, _p, _i, _p, _i, _p, _f, _i, _i, _i, _i, _p]),
+    "xs_row_stats": (_i, [_p, _p, _p, _f, _i, _p]),
+    "xs_gemm_ln_folded": (_i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "xs_flash_attn": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _f, _i, _p]),
     "xs_attn_set_optimistic": (None, [_i]),
     "xs_attn_set_layout": (None, [_i]),

@@ -79,6 +79,11 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
 
 // kernels (defined in the other translation units)
 int gemm_tc(const void*, int, const void*, int, const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int gemm_tc_residual_stats(const void*, int, const void*, int, const float*, float*, int, void*, int, float*, float, int,
+                           int, int, cudaStream_t);
+int gemm_tc_ln_folded(const void*, int, const void*, int, const float*, const float*, const float*, void*, int, int, int,
+                      int, int, cudaStream_t);
+int rows_stats(const float*, void*, float*, float, int, cudaStream_t);
 int gemm_tc_residual_ln(const void*, int, const void*, int, const float*, float*, int, const float*, const float*, float,
                         void*, int, int, int, int, cudaStream_t);
 int head_jigsaw_tc(const void*, int, const void*, int, const float*, float*, int, int, int, int, int, float, int,
@@ -232,6 +237,33 @@ int xs_gemm_bias_residual_ln(const void* A, int lda, const void* W, int ldw, con
   if (r2) return r2;
   XS_CHECK_ARG(ldh == 384 && ldy == 384, "gemm_bias_residual_ln: the unfused path needs dense rows");
   return rows_add_ln(h, nullptr, nullptr, gamma, beta, eps, y, nullptr, M, XS_BF16, st);
+}
+
+int xs_gemm_bias_residual_stats(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
+                                void* hb, int ldhb, float* stats, float eps, int M, int N, int K, int dtype,
+                                xs_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XS_CHECK_ARG(dtype == XS_BF16, "gemm_bias_residual_stats: bf16 operands only");
+  XS_CHECK_ARG(N == 384 && ldhb >= N && ldh >= N, "gemm_bias_residual_stats: N must be 384 (LayerNorm width), got %d", N);
+  const int rc = gemm_tc_residual_stats(A, lda, W, ldw, bias, h, ldh, hb, ldhb, stats, eps, M, N, K, st);
+  if (rc != 1) return rc;
+  // shapes the fused epilogue does not cover (few rows): the same result in two launches
+  const int r2 = gemm_tc(A, lda, W, ldw, bias, h, ldh, M, N, K, ACT_NONE, 0, 2, st);
+  if (r2) return r2;
+  XS_CHECK_ARG(ldh == 384 && ldhb == 384, "gemm_bias_residual_stats: the unfused path needs dense rows");
+  return rows_stats(h, hb, stats, eps, M, st);
+}
+
+int xs_row_stats(const float* h, void* hb, float* stats, float eps, int rows, xs_stream_t stream) {
+  return rows_stats(h, hb, stats, eps, rows, static_cast<cudaStream_t>(stream));
+}
+
+int xs_gemm_ln_folded(const void* A, int lda, const void* W, int ldw, const float* c0, const float* c1,
+                      const float* stats, void* out, int ldc, int M, int N, int K, int act, int dtype,
+                      xs_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XS_CHECK_ARG(dtype == XS_BF16, "gemm_ln_folded: bf16 operands only");
+  return gemm_tc_ln_folded(A, lda, W, ldw, c0, c1, stats, out, ldc, M, N, K, act, st);
 }
 
 int xs_flash_attn(const void* q, const void* k, const void* v, void* o, float* lse, int B, int heads, int Lq, int Lk,

@@ -38,7 +38,9 @@ void set_last_error(const char* fmt, ...);
 #define XS_LAUNCH_CHECK() XS_CUDA(cudaGetLastError())
 
 enum DType : int { XS_BF16 = 0, XS_F32 = 1, XS_TF32 = 2, XS_F16 = 3 };
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_LEAKY = 3 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_LEAKY = 3,
+                 // LayerNorm folded into the GEMM (xs_gemm_ln_folded): per row rstd * (acc - mean * c1[n]) + c0[n], then the activation
+                 ACT_LN_NONE = 4, ACT_LN_GELU = 5 };
 
 int num_sms();
 
@@ -188,6 +190,16 @@ __device__ __forceinline__ float2 bias_act2(float v0, float v1, float b0, float 
   const float2 x = fadd2(make_float2(v0, v1), make_float2(b0, b1));  // one FADD2 for the two bias adds
   if constexpr (ACT == ACT_GELU) return gelu_erf_fast2(x);
   else return make_float2(apply_act<ACT>(x.x), apply_act<ACT>(x.y));
+}
+
+// act(acc * rstd + (rm * c1 + c0)) for a pair: the LayerNorm-folded epilogue (rm = -rstd * mean of the row)
+template <int ACT>
+__device__ __forceinline__ float2 lnfold_act2(float v0, float v1, float rstd, float rm, float c1a, float c1b, float c0a,
+                                              float c0b) {
+  const float2 t = ffma2(make_float2(rm, rm), make_float2(c1a, c1b), make_float2(c0a, c0b));
+  const float2 x = ffma2(make_float2(v0, v1), make_float2(rstd, rstd), t);
+  if constexpr (ACT == ACT_LN_GELU) return gelu_erf_fast2(x);
+  else return x;
 }
 
 // ---------------------------------------------------------------------------------------------

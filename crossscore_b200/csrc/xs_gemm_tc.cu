@@ -86,13 +86,17 @@ struct GemmSmem {
 // (its own TMA stores, L2 hits) tile by tile, normalises and emits y = LN(h) in bf16 through a second tensor map.
 // The LayerNorm kernel launch and its HBM read of h disappear (modeling_dinov2.py:367-386: norm2 after the attention
 // residual, the next layer's norm1 after the MLP residual).
+// LNF = 2 (same shapes): the epilogue only MEASURES the rows -- it emits a bf16 copy of the updated residual stream and
+// (mean, rstd) per row; the LayerNorm itself is folded into the GEMM that consumes it (ACT_LN_*: gamma folded into the
+// weights, rstd * (acc - mean * c1[n]) + c0[n] in that GEMM's epilogue), so no second pass and no LayerNorm kernel.
 struct LnParams {
-  const float* gamma;
+  const float* gamma;   // LNF = 1: LayerNorm weight.  ACT_LN_* consumer: c1[n] = sum_k bf16(gamma[k] W[n,k])
   const float* beta;
   float eps;
   const float* h;       // the residual stream the epilogue has just updated (row pitch ldh floats)
-  __nv_bfloat16* y;     // LayerNorm output (row pitch ldy elements)
+  __nv_bfloat16* y;     // LNF = 1: LayerNorm output; LNF = 2: bf16 copy of h (row pitch ldy elements)
   int ldh, ldy;
+  float2* stats;        // LNF = 2: (mean, rstd) per row, written; ACT_LN_* consumer: read
 };
 
 template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2, int LNF = 0>
@@ -141,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     if constexpr (EPI == EPI_STORE) tma_prefetch_desc(&tmC);
-    if constexpr (LNF) tma_prefetch_desc(&tmY);
+    if constexpr (LNF == 1) tma_prefetch_desc(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -322,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if constexpr (OUT == OUT_F32_ADD && EPI == EPI_STORE) {
         constexpr int MY_STEPS_ = BN / 64;
         int t, sidx;
-        if constexpr (LNF) {
+        if constexpr (LNF == 1) {
           // per row block: pass 1 = the residual tiles of its num_n * MY_STEPS_ steps, pass 2 = the same tiles again
           // (now holding h + delta, written by this warp's own TMA stores)
           const int spr = num_n * MY_STEPS_;
@@ -366,6 +370,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         static_assert(NSTEP % 2 == 0, "BN must be a multiple of 64");
         uint8_t* my_staging = staging + (warp - 4) * (2 * L::WARP_STAGE_BYTES);
         const int m0 = m_blk * GEMM_BM + q * 32;
+        [[maybe_unused]] float ln_rstd = 0.f, ln_rm = 0.f;
+        if constexpr (ACT == ACT_LN_NONE || ACT == ACT_LN_GELU) {  // thread == row: its (mean, rstd), once per tile
+          if (m0 + lane < M) {
+            const float2 st = __ldg(lnp.stats + m0 + lane);
+            ln_rstd = st.y;
+            ln_rm = -st.y * st.x;
+          }
+        }
         uint32_t v[2][32];
         tmem_ld32(taddr0 + half * 32, v[0]);
 #pragma unroll
@@ -388,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // step's residual tile into it; then wait for this step's tile (requested one step ago)
             if (lane == 0) {
               tma_store_wait_read<0>();
-              if constexpr (LNF) {
+              if constexpr (LNF == 1) {
                 // the next load may be a pass-2 load (last pass-1 step of the row block): the tile it re-reads was
                 // stored 2 * num_n * MY_STEPS - 1 steps ago; at most 4 younger store groups may still be pending
                 if (n_blk == num_n - 1 && i == MY_STEPS - 1) tma_store_wait_all<4>();
@@ -409,15 +421,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (OUT == OUT_BF16 || OUT == OUT_F16) {
             // 64-byte rows, 64B swizzle: 16-byte chunk index XOR ((row >> 1) & 3); conflict-free for thread == row
             uint8_t* rp = srow + lane * 64;
+            [[maybe_unused]] const float4* c14 = reinterpret_cast<const float4*>(lnp.gamma + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 ba = __ldg(b4 + j * 2), bb = __ldg(b4 + j * 2 + 1);
               const int o = j * 8;
               uint4 pk;
-              const float2 r0 = bias_act2<ACT>(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1]), ba.x, ba.y);
-              const float2 r1 = bias_act2<ACT>(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3]), ba.z, ba.w);
-              const float2 r2 = bias_act2<ACT>(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5]), bb.x, bb.y);
-              const float2 r3 = bias_act2<ACT>(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7]), bb.z, bb.w);
+              float2 r0, r1, r2, r3;
+              if constexpr (ACT == ACT_LN_NONE || ACT == ACT_LN_GELU) {
+                const float4 ca = __ldg(c14 + j * 2), cb = __ldg(c14 + j * 2 + 1);
+                r0 = lnfold_act2<ACT>(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1]), ln_rstd, ln_rm, ca.x, ca.y, ba.x, ba.y);
+                r1 = lnfold_act2<ACT>(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3]), ln_rstd, ln_rm, ca.z, ca.w, ba.z, ba.w);
+                r2 = lnfold_act2<ACT>(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5]), ln_rstd, ln_rm, cb.x, cb.y, bb.x, bb.y);
+                r3 = lnfold_act2<ACT>(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7]), ln_rstd, ln_rm, cb.z, cb.w, bb.z, bb.w);
+              } else {
+                r0 = bias_act2<ACT>(__uint_as_float(vv[o + 0]), __uint_as_float(vv[o + 1]), ba.x, ba.y);
+                r1 = bias_act2<ACT>(__uint_as_float(vv[o + 2]), __uint_as_float(vv[o + 3]), ba.z, ba.w);
+                r2 = bias_act2<ACT>(__uint_as_float(vv[o + 4]), __uint_as_float(vv[o + 5]), bb.x, bb.y);
+                r3 = bias_act2<ACT>(__uint_as_float(vv[o + 6]), __uint_as_float(vv[o + 7]), bb.z, bb.w);
+              }
               pk.x = pack_out16<OUT>(r0.x, r0.y);
               pk.y = pack_out16<OUT>(r1.x, r1.y);
               pk.z = pack_out16<OUT>(r2.x, r2.y);
@@ -427,6 +449,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             // 128-byte rows, 128B swizzle: 16-byte chunk index XOR (row & 7)
             uint8_t* rp = srow + lane * 128;
+            [[maybe_unused]] uint32_t hb_lo0 = 0u, hb_lo1 = 0u;
+            [[maybe_unused]] uint4* hb_row = nullptr;
+            if constexpr (LNF == 2)
+              hb_row = reinterpret_cast<uint4*>(lnp.y + static_cast<size_t>(m0 + lane) * lnp.ldy + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 ba = __ldg(b4 + j);
@@ -449,6 +475,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float d0 = o4.x - ln_c, d1 = o4.y - ln_c, d2 = o4.z - ln_c, d3 = o4.w - ln_c;
                 ln_s1 += (d0 + d1) + (d2 + d3);
                 ln_s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+              }
+              if constexpr (LNF == 2) {
+                // bf16 copy of the updated rows, straight from registers: 64 contiguous bytes per thread and step
+                if (j & 1) {
+                  if (m0 + lane < M)
+                    hb_row[j >> 1] = make_uint4(hb_lo0, hb_lo1, pack_bf16x2(o4.x, o4.y), pack_bf16x2(o4.z, o4.w));
+                } else {
+                  hb_lo0 = pack_bf16x2(o4.x, o4.y);
+                  hb_lo1 = pack_bf16x2(o4.z, o4.w);
+                }
               }
               *sp = o4;
             }
@@ -476,12 +512,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float mean = mean_t + 0.5f * dm;
             const float var = (m2_t + other.y + dm * dm * (0.5f * nh)) / (2.0f * nh);
             const float rstd = rsqrtf(var + lnp.eps);
+            if constexpr (LNF == 2) {
+              if (half == 0 && m0 + lane < M) lnp.stats[m0 + lane] = make_float2(mean, rstd);
+            }
             // ---- pass 2: re-read the updated tiles (this warp's own TMA stores: L2 hits) through the same
             //      double-buffered TMA pipeline, normalise, store y (bf16) through the second tensor map.
             //      (A variant with plain per-thread vector loads instead of TMA was 2x slower: thread == row makes every
             //      lane touch its own cache line.  profiles/r2_experiments.txt) ----
 #pragma unroll 1
-            for (int s2 = 0; s2 < num_n * MY_STEPS; ++s2) {
+            for (int s2 = 0; LNF == 1 && s2 < num_n * MY_STEPS; ++s2) {
               const int nb2 = s2 / MY_STEPS, c2 = 2 * (s2 % MY_STEPS) + half;
               const uint32_t buf = chunk_counter & 1;
               if (lane == 0) {
@@ -594,7 +633,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int STAGES, int EPI, int ACT, int IN, int OUT, int CTA2 = 0, int LNF = 0>
 static int launch_gemm(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldc, int M,
                        int N, int K, JigsawParams jp, cudaStream_t stream, void* y = nullptr, int ldy = 0,
-                       LnParams lnp = LnParams{nullptr, nullptr, 0.f, nullptr, nullptr, 0, 0}) {
+                       LnParams lnp = LnParams{nullptr, nullptr, 0.f, nullptr, nullptr, 0, 0, nullptr}) {
   using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT, LNF>;
   constexpr int IN_B = (IN == IN_TF32) ? 4 : 2;
   constexpr int OUT_B = (OUT == OUT_F32 || OUT == OUT_F32_ADD) ? 4 : 2;
@@ -623,8 +662,8 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const flo
   } else {
     tmC = tmA;  // unused
   }
-  CUtensorMap tmY = tmC;  // unused unless LNF
-  if constexpr (LNF) {
+  CUtensorMap tmY = tmC;  // unused unless LNF == 1
+  if constexpr (LNF == 1) {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)ldy * 2};
     uint32_t box[2] = {32, 32};
@@ -784,12 +823,70 @@ int gemm_tc_residual_ln(const void* A, int lda, const void* W, int ldw, const fl
   JigsawParams jp{};
   void* out = h;
   const int ldc = ldh;
-  const LnParams lnp{gamma, beta, eps, h, static_cast<__nv_bfloat16*>(y), ldh, ldy};
+  const LnParams lnp{gamma, beta, eps, h, static_cast<__nv_bfloat16*>(y), ldh, ldy, nullptr};
   if (K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
     return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 2, 1>(XS_GEMM_ARGS, y, ldy, lnp);
   if (K >= 1024 && num_m2 >= num_sms() / 2)
     return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 1, 1>(XS_GEMM_ARGS, y, ldy, lnp);
   return 1;
+}
+
+// h (fp32, in place) += A W^T + bias; hb (bf16) = h; stats[r] = (mean, rstd) of row r of h.  The producer half of the
+// folded LayerNorm (LNF = 2).  Returns 1 when the shape is not covered (same coverage as gemm_tc_residual_ln).
+int gemm_tc_residual_stats(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
+                           void* hb, int ldhb, float* stats, float eps, int M, int N, int K, cudaStream_t stream) {
+  XS_CHECK_ARG(M > 0 && K > 0, "gemm_residual_stats: empty problem");
+  XS_CHECK_ARG((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && (ldh % 4) == 0 && (ldhb % 8) == 0,
+               "gemm_residual_stats: row pitches must be multiples of 16 bytes");
+  XS_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(h) |
+                 reinterpret_cast<uintptr_t>(hb) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(stats)) & 15) == 0,
+               "gemm_residual_stats: pointers must be 16-byte aligned");
+  if (N != 384) return 1;
+  const int num_m2 = (M + 255) / 256;
+  JigsawParams jp{};
+  void* out = h;
+  const int ldc = ldh;
+  const LnParams lnp{nullptr, nullptr, eps, h, static_cast<__nv_bfloat16*>(hb), ldh, ldhb, reinterpret_cast<float2*>(stats)};
+  if (K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
+    return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 2, 2>(XS_GEMM_ARGS, hb, ldhb, lnp);
+  if (K >= 1024 && num_m2 >= num_sms() / 2)
+    return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 1, 2>(XS_GEMM_ARGS, hb, ldhb, lnp);
+  return 1;
+}
+
+// out (bf16) = act(LayerNorm(h) W^T + b) with the LayerNorm folded in: A = bf16 copy of h, W = bf16(gamma * W), and per
+// row rstd * (acc - mean * c1[n]) + c0[n] in the epilogue (c1[n] = sum_k W[n,k] of the folded bf16 weight, c0 = W beta + b).
+// The consumer half of the folded LayerNorm (A-stationary CTA pairs for K <= 384 and many rows, else independent CTAs).
+int gemm_tc_ln_folded(const void* A, int lda, const void* W, int ldw, const float* c0, const float* c1,
+                      const float* stats, void* out, int ldc, int M, int N, int K, int act, cudaStream_t stream) {
+  XS_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_ln_folded: empty problem");
+  XS_CHECK_ARG(act == ACT_NONE || act == ACT_GELU, "gemm_ln_folded: act must be NONE or GELU, got %d", act);
+  XS_CHECK_ARG((K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && (ldc % 8) == 0,
+               "gemm_ln_folded: row pitches must be multiples of 16 bytes");
+  XS_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) |
+                 reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(stats)) & 15) == 0,
+               "gemm_ln_folded: pointers must be 16-byte aligned");
+  const bool use192 = (N % 192 == 0) && (N % 256 != 0 || N < 1024);
+  XS_CHECK_ARG(use192 || N % 256 == 0, "gemm_ln_folded: N=%d must be a multiple of 192 or 256", N);
+  const int num_m2 = (M + 255) / 256;
+  JigsawParams jp{};
+  const float* bias = c0;
+  const LnParams lnp{c1, nullptr, 0.f, nullptr, nullptr, 0, 0,
+                     const_cast<float2*>(reinterpret_cast<const float2*>(stats))};
+  if (!(K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)) {  // few rows or long K: independent CTAs
+    if (act == ACT_GELU) {
+      if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_LN_GELU, IN_BF16, OUT_BF16>(XS_GEMM_ARGS, nullptr, 0, lnp);
+      return launch_gemm<256, 4, EPI_STORE, ACT_LN_GELU, IN_BF16, OUT_BF16>(XS_GEMM_ARGS, nullptr, 0, lnp);
+    }
+    if (use192) return launch_gemm<192, 4, EPI_STORE, ACT_LN_NONE, IN_BF16, OUT_BF16>(XS_GEMM_ARGS, nullptr, 0, lnp);
+    return launch_gemm<256, 4, EPI_STORE, ACT_LN_NONE, IN_BF16, OUT_BF16>(XS_GEMM_ARGS, nullptr, 0, lnp);
+  }
+  if (act == ACT_GELU) {
+    if (use192) return launch_gemm<192, 8, EPI_STORE, ACT_LN_GELU, IN_BF16, OUT_BF16, 2>(XS_GEMM_ARGS, nullptr, 0, lnp);
+    return launch_gemm<256, 6, EPI_STORE, ACT_LN_GELU, IN_BF16, OUT_BF16, 2>(XS_GEMM_ARGS, nullptr, 0, lnp);
+  }
+  if (use192) return launch_gemm<192, 8, EPI_STORE, ACT_LN_NONE, IN_BF16, OUT_BF16, 2>(XS_GEMM_ARGS, nullptr, 0, lnp);
+  return launch_gemm<256, 6, EPI_STORE, ACT_LN_NONE, IN_BF16, OUT_BF16, 2>(XS_GEMM_ARGS, nullptr, 0, lnp);
 }
 
 // head.2 Linear (384 -> 196, weight rows padded to 224) + sigmoid/tanh (+pow) + jigsaw scatter

@@ -106,6 +106,35 @@ __global__ void __launch_bounds__(256) add_ln_kernel(const float* __restrict__ r
 }
 
 // ---------------------------------------------------------------------------------------------
+// The folded LayerNorm's producer as a stand-alone pass (shapes the fused GEMM epilogue does not cover, and its check):
+// hb = bf16(h), stats[row] = (mean, rstd) of the fp32 row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ hb,
+                                                        float2* __restrict__ stats, float eps, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t base = static_cast<size_t>(row) * C;
+  Row12 x;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    x.v[i] = *reinterpret_cast<const float4*>(h + base + col_of(lane, i));
+    s += x.v[i].x + x.v[i].y + x.v[i].z + x.v[i].w;
+    Pack4<__nv_bfloat16>::store(hb + base + col_of(lane, i), x.v[i]);
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a = x.v[i].x - mean, b = x.v[i].y - mean, c = x.v[i].z - mean, d = x.v[i].w - mean;
+    ss += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+// ---------------------------------------------------------------------------------------------
 // DINOv2 embeddings: h[i,0] = cls + pos[0]; h[i,1+p] = tok[i,p] + pos[1+p];  y = LN(h; layer-0 norm1)
 // ---------------------------------------------------------------------------------------------
 template <typename AT, typename TT>
@@ -480,6 +509,14 @@ int rows_add_ln(const float* res_in, const void* delta, float* res_out, const fl
   const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   XS_DISPATCH_AT(dtype, (add_ln_kernel<AT><<<grid, 256, 0, stream>>>(res_in, static_cast<const AT*>(delta), res_out,
                                                                      gamma, beta, eps, static_cast<AT*>(y), y32, rows)));
+  XS_LAUNCH_CHECK();
+  return 0;
+}
+
+int rows_stats(const float* h, void* hb, float* stats, float eps, int rows, cudaStream_t stream) {
+  XS_CHECK_ARG(rows > 0, "row_stats: rows=%d", rows);
+  const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  row_stats_kernel<<<grid, 256, 0, stream>>>(h, static_cast<__nv_bfloat16*>(hb), reinterpret_cast<float2*>(stats), eps, rows);
   XS_LAUNCH_CHECK();
   return 0;
 }

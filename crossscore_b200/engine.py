@@ -156,6 +156,20 @@ class PackedWeights:
                 w1=W(f32(p + "mlp.fc1.weight")), b1=f32(p + "mlp.fc1.bias"),
                 w2=W(f32(p + "mlp.fc2.weight") * lam2[:, None]), b2=(f32(p + "mlp.fc2.bias") * lam2).contiguous(),
             )
+            if precision == "bf16":
+                # LayerNorm folded into the Linear that follows it (xs_gemm_ln_folded): gamma into the weight (fp32 product,
+                # then one bf16 rounding), c1 = row sums of the ROUNDED weight (the mean correction must match what the MMA
+                # sums), c0 = W beta + b.  norm1 -> q|k|v, norm2 -> fc1 (modeling_dinov2.py:367-386).
+                wq32 = torch.cat([f32(p + "attention.attention.query.weight") * qs_dino,
+                                  f32(p + "attention.attention.key.weight"),
+                                  f32(p + "attention.attention.value.weight")], 0)
+                L["wqkv_f"] = W(wq32 * L["ln1_g"][None, :])
+                L["c1_qkv"] = L["wqkv_f"].float().sum(-1).contiguous()
+                L["c0_qkv"] = (wq32 @ L["ln1_b"] + L["bqkv"]).contiguous()
+                w1_32 = f32(p + "mlp.fc1.weight")
+                L["w1_f"] = W(w1_32 * L["ln2_g"][None, :])
+                L["c1_fc1"] = L["w1_f"].float().sum(-1).contiguous()
+                L["c0_fc1"] = (w1_32 @ L["ln2_b"] + L["b1"]).contiguous()
             self.layers.append(L)
         self.lnf_g, self.lnf_b = f32(b + "layernorm.weight"), f32(b + "layernorm.bias")
         self.pe_table = f32("pos_enc_fn.PE")[0].contiguous()  # (pe_h, pe_w, C)
@@ -256,6 +270,13 @@ class Engine:
         # Parity-green and 23 launches fewer, but the step time is the same in an in-run A/B (28.46-28.58 vs 28.43-28.47
         # ms: the second pass over the row block costs what the LayerNorm kernel did), so the proven plan stays default.
         self.fuse_ln = self.fuse_residual and os.environ.get("XS_FUSE_LN", "0") == "1"
+        # XS_FOLD_LN=1 (opt-in, experimental): for batches that fill the GPU the LayerNorms of the DINOv2 blocks are folded into
+        # the GEMMs around them -- the residual epilogue emits a bf16 copy of h and per-row (mean, rstd)
+        # (xs_gemm_bias_residual_stats), the consuming q|k|v / fc1 GEMM normalises in its epilogue (xs_gemm_ln_folded).
+        # Parity-tested, but measured SLOWER (27.94 vs 27.68 ms per step in one run: the 23 LayerNorm launches, 2.3 ms, are
+        # gone, the four GEMMs' epilogues grow by 2.6 ms) and less precise with outlier channels (h instead of LayerNorm(h)
+        # is what gets rounded to bf16: 5.9e-2 max-abs between the plans on the outlier weights, 5.8e-3 on benign ones).
+        self.fold_ln = self.fuse_residual and os.environ.get("XS_FOLD_LN", "0") == "1"
         self.prof = None  # list of (tag, algorithmic flops, algorithmic bytes, start event, stop event) when profiling
         self._last_stream = None   # the engine's scratch buffers are shared by every call: see serialise()
         self._last_event = None
@@ -321,6 +342,29 @@ class Engine:
         with self._op(tag + "_ln", 2.0 * M * N * K):
             call("xs_gemm_bias_residual_ln", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(h),
                  h.stride(0), _ptr(g), _ptr(b), eps, _ptr(y), y.stride(0), M, N, K, DT_BF16, st)
+
+    @staticmethod
+    def fold_ln_rows(rows: int) -> bool:
+        """Row counts for which the folded-LayerNorm plan is used: the fused statistics epilogue needs every CTA pair to
+        own a 256-row block (xs_gemm_tc.cu: num_m2 >= SMs / 2); below that the plain plan is as fast."""
+        return (rows + 255) // 256 >= NUM_SMS_HINT // 2
+
+    def _gemm_residual_stats(self, A, Wt, bias, h, hb, stats, eps, st, tag="gemm"):
+        """h (fp32, in place) += A @ Wt^T + bias;  hb = bf16(h);  stats = (mean, rstd) per row of h."""
+        M, K = A.shape
+        N = Wt.shape[0]
+        assert A.dtype == torch.bfloat16 and h.dtype == torch.float32 and hb.dtype == torch.bfloat16
+        with self._op(tag, 2.0 * M * N * K):
+            call("xs_gemm_bias_residual_stats", _ptr(A), A.stride(0), _ptr(Wt), Wt.stride(0), _ptr(bias), _ptr(h),
+                 h.stride(0), _ptr(hb), hb.stride(0), _ptr(stats), eps, M, N, K, DT_BF16, st)
+
+    def _gemm_ln_folded(self, hb, Wf, c0, c1, stats, out, act, st, tag="gemm"):
+        """out = act(LayerNorm(h) @ W^T + b) from the bf16 copy of h, the gamma-folded weight and the row statistics."""
+        M, K = hb.shape
+        N = Wf.shape[0]
+        with self._op(tag, 2.0 * M * N * K):
+            call("xs_gemm_ln_folded", _ptr(hb), hb.stride(0), _ptr(Wf), Wf.stride(0), _ptr(c0), _ptr(c1), _ptr(stats),
+                 _ptr(out), out.stride(0), M, N, K, act, DT_BF16, st)
 
     def _ln(self, res_in, delta, res_out, g, b, eps, y, y32, rows, st):
         dt = DT_BF16 if (delta is not None and delta.dtype == torch.bfloat16) or \
@@ -393,10 +437,25 @@ class Engine:
             call("xs_embed_cls_pos_ln", _ptr(tok), DT_F32, _ptr(w.cls), _ptr(pos), _ptr(h), _ptr(L0["ln1_g"]),
                  _ptr(L0["ln1_b"]), DINO_EPS, _ptr(y), I, P, self.dt, st)
         fused = self.dt == DT_BF16 and self.fuse_residual
+        fold = fused and self.fold_ln and not self.fuse_ln and self.fold_ln_rows(R)
+        stats = self._buf("ln_stats", (R, 2), torch.float32) if fold else None
         for l, L in enumerate(w.layers):
-            self._gemm(y, L["wqkv"], L["bqkv"], qkv, ACT_NONE, st, tag="gemm_dino_qkv")
+            if fold and l > 0:  # y holds bf16(h) and stats its row statistics (fc2 epilogue of the previous layer)
+                self._gemm_ln_folded(y, L["wqkv_f"], L["c0_qkv"], L["c1_qkv"], stats, qkv, ACT_NONE, st, tag="gemm_dino_qkv")
+            else:
+                self._gemm(y, L["wqkv"], L["bqkv"], qkv, ACT_NONE, st, tag="gemm_dino_qkv")
             self._attn(qkv[:, 0:], qkv[:, C:], qkv[:, 2 * C:], att, I, DINO_HEADS, T, T, 64, 64,
                        3 * C, T * 3 * C, 3 * C, T * 3 * C, False, st, name="dino")
+            if fold:
+                # h += att Wo^T + bo with y = bf16(h) and the row statistics out of the same epilogue; norm2 happens inside
+                # fc1's epilogue; the same for fc2 -> next layer's norm1 -> q|k|v
+                self._gemm_residual_stats(att, L["wo"], L["bo"], h, y, stats, DINO_EPS, st, tag="gemm_dino_proj")
+                self._gemm_ln_folded(y, L["w1_f"], L["c0_fc1"], L["c1_fc1"], stats, g1, ACT_GELU, st, tag="gemm_dino_fc1")
+                if l + 1 < DINO_LAYERS:
+                    self._gemm_residual_stats(g1, L["w2"], L["b2"], h, y, stats, DINO_EPS, st, tag="gemm_dino_fc2")
+                else:
+                    self._gemm_residual(g1, L["w2"], L["b2"], h, st, tag="gemm_dino_fc2")
+                continue
             if fused and self.fuse_ln:
                 # residual add AND the following LayerNorm in the GEMM epilogue: h += att Wo^T + bo; y = LN2(h)
                 self._gemm_residual_ln(att, L["wo"], L["bo"], h, L["ln2_g"], L["ln2_b"], DINO_EPS, y, st,

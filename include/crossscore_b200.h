@@ -126,6 +126,24 @@ int xs_gemm_bias_residual_ln(const void* A, int lda, const void* W, int ldw, con
                              const float* gamma, const float* beta, float eps, void* y, int ldy, int M, int N, int K,
                              int dtype, xs_stream_t stream);
 
+/* K6+K2 / K7+K2 with the LayerNorm FOLDED into the GEMM that consumes it (the default plan of the bf16 mode for large
+ *     batches).  The same two reference steps as above (modeling_dinov2.py:367-386, 312-328, 203-234), split differently:
+ *       producer:  h (fp32, in place) += A @ W^T + bias;  hb (bf16) = h;  stats[r] = (mean_r, rstd_r) of row r of h
+ *       consumer:  out (bf16) = act( rstd_r * (hb @ Wf^T - mean_r * c1) + c0 )
+ *     with Wf = bf16(gamma * W) (LayerNorm weight folded into the next Linear's weight), c1[n] = sum_k Wf[n,k] and
+ *     c0 = W beta + b, which equals act(LayerNorm(h) @ W^T + b) up to the rounding of h (instead of LayerNorm(h)) to
+ *     bf16.  No LayerNorm kernel, no second pass: the statistics come out of the residual epilogue (one CTA sees whole
+ *     rows), the normalisation is two FMAs per element in the consumer's epilogue.  stats: (M, 2) fp32.  N = 384 for
+ *     the producer; act = XS_ACT_NONE or XS_ACT_GELU for the consumer.  xs_row_stats is the producer's second half as a
+ *     stand-alone pass (what the producer runs for row counts its fused epilogue does not cover). */
+int xs_gemm_bias_residual_stats(const void* A, int lda, const void* W, int ldw, const float* bias, float* h, int ldh,
+                                void* hb, int ldhb, float* stats, float eps, int M, int N, int K, int dtype,
+                                xs_stream_t stream);
+int xs_row_stats(const float* h, void* hb, float* stats, float eps, int rows, xs_stream_t stream);
+int xs_gemm_ln_folded(const void* A, int lda, const void* W, int ldw, const float* c0, const float* c1,
+                      const float* stats, void* out, int ldc, int M, int N, int K, int act, int dtype,
+                      xs_stream_t stream);
+
 /* K4,K9,K10  O = softmax(Q K^T * scale) V  per (batch, head), no mask
  *     (modeling_dinov2.py:203-234; $SP/torch/nn/functional.py:6630-6692 via transformer.py:182-205).
  *     head_slot: column pitch between heads in q/k/v rows (bf16: must be 64).  kv_shared: all batches

@@ -177,6 +177,67 @@ def test_gemm_bias_residual_ln(M, K):
     assert (err <= 0.02 + 0.01 * yref.abs()).all(), err.max().item()
 
 
+@pytest.mark.parametrize("M,K", [(20000, 384), (19001, 384), (20000, 1536), (37931, 1536), (1000, 384), (9000, 1536)])
+def test_gemm_bias_residual_stats(M, K):
+    """Producer half of the folded LayerNorm: h += A W^T + b, hb = bf16(h), stats = (mean, rstd) per row -- fused epilogue
+    for large M (both CTA-pair modes, ragged row tails), two launches otherwise.  Rows carry a large common offset and
+    outlier channels."""
+    N = 384
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    W = rnd(N, K, seed=2, scale=0.05, dtype=torch.bfloat16)
+    b = rnd(N, seed=3)
+    h0 = rnd(M, N, seed=4, scale=2.0) + 7.0
+    h0[:, [5, 133, 301]] *= 40.0
+    h = h0.clone()
+    hb = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    stats = torch.full((M, 2), float("nan"), device=DEV)
+    call("xs_gemm_bias_residual_stats", P(A), K, P(W), K, P(b), P(h), N, P(hb), N, P(stats), 1e-6, M, N, K, DT_BF16, st())
+    torch.cuda.synchronize()
+    href = h0.double() + A.double() @ W.double().T + b.double()
+    assert ((h.double() - href).abs() <= 2e-3 + 1e-5 * href.abs()).all()
+    assert torch.equal(hb, h.bfloat16())                       # the copy is the rounding of what was stored
+    mean = h.double().mean(-1)
+    rstd = torch.rsqrt(h.double().var(-1, unbiased=False) + 1e-6)
+    assert torch.isfinite(stats).all()
+    assert ((stats[:, 0].double() - mean).abs() <= 1e-4 * (1 + mean.abs())).all()
+    assert ((stats[:, 1].double() - rstd).abs() <= 1e-4 * rstd).all()
+
+
+@pytest.mark.parametrize("M,N,act", [(20000, 1152, ACT_NONE), (19001, 1536, ACT_GELU), (37931, 1152, ACT_NONE),
+                                     (1000, 1536, ACT_GELU), (777, 1152, ACT_NONE)])
+def test_gemm_ln_folded(M, N, act):
+    """Consumer half: act(LayerNorm(h) W^T + b) from hb = bf16(h), Wf = bf16(gamma * W), c1 = row sums of Wf,
+    c0 = W beta + b and the per-row (mean, rstd).  Checked tightly against the folded formula in fp64 on the same bf16
+    operands, and at bf16 level against the LayerNorm-then-Linear it replaces."""
+    K = 384
+    h = rnd(M, K, seed=4, scale=2.0) + 3.0
+    h[:, [5, 133, 301]] *= 20.0
+    g, be = rnd(K, seed=5) * 0.2 + 1, rnd(K, seed=6, scale=0.1)
+    W = rnd(N, K, seed=2, scale=0.05)
+    b = rnd(N, seed=3)
+    Wf = (W * g[None, :]).bfloat16().contiguous()
+    c1 = Wf.float().sum(-1).contiguous()
+    c0 = (W @ be + b).contiguous()
+    hb = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
+    stats = torch.empty(M, 2, device=DEV)
+    call("xs_row_stats", P(h), P(hb), P(stats), 1e-6, M, st())
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call("xs_gemm_ln_folded", P(hb), K, P(Wf), K, P(c0), P(c1), P(stats), P(out), N, M, N, K, act, DT_BF16, st())
+    torch.cuda.synchronize()
+    assert torch.equal(hb, h.bfloat16())
+    f = (lambda x: torch.nn.functional.gelu(x)) if act == ACT_GELU else (lambda x: x)
+    mean, rstd = stats[:, :1].double(), stats[:, 1:].double()
+    folded = f(rstd * (hb.double() @ Wf.double().T - mean * c1.double()) + c0.double())
+    err = (out.double() - folded).abs()
+    assert torch.isfinite(out).all()
+    assert (err <= 2e-3 + 6e-3 * folded.abs()).all(), err.max().item()   # bf16 rounding of the output
+    ref = f(torch.nn.functional.layer_norm(h.double(), (K,), g.double(), be.double(), 1e-6) @ W.double().T + b.double())
+    err = (out.double() - ref).abs()
+    assert err.mean() < 6e-3 and (err <= 0.06 + 0.02 * ref.abs()).all(), (err.mean().item(), err.max().item())
+    with pytest.raises(_lib.XsError):
+        call("xs_gemm_ln_folded", P(hb), K, P(Wf), K, P(c0), P(c1), P(stats), P(out), N, M, N, K, ACT_RELU, DT_BF16, st())
+
+
 def test_gemm_bf16_rejects_bad_shapes():
     A = rnd(128, 384, dtype=torch.bfloat16)
     W = rnd(200, 384, dtype=torch.bfloat16)
@@ -195,7 +256,7 @@ def layout(request):
     CTA sharing 128-key blocks (xs_attn_tc2.cu)."""
     _lib.load().xs_attn_set_layout(request.param)
     yield request.param
-    _lib.load().xs_attn_set_layout(0)
+    _lib.load().xs_attn_set_layout(1)  # the library default
 
 
 def attn_ref(q, k, v, scale):
