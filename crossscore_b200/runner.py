@@ -4,11 +4,50 @@ This is the call a user of the reference makes per batch -- Lightning moves ``ba
 ``batch["reference/cross/imgs"]`` to the device, runs ``CrossScoreNet.forward`` and the writers read the
 score map back (task/core.py:266-272, utils/io/batch_writer.py:133-135).  ``HostScorer`` does the same with
 double-buffered device inputs: the H2D copy of batch i+1 runs on a copy stream while batch i computes, and
-the score maps are read back to pinned host memory.
+the score maps of batch i are read back to pinned host memory on a third stream while batch i+1 computes (the
+forward's output buffer is copied aside on the device first; a read-back queued on the compute stream would hold
+up the next forward for the 34 MB PCIe transfer).
 """
 from __future__ import annotations
 
 import torch
+
+
+class _ReadBack:
+    """Device -> pinned host copies on their own stream, double-buffered through device staging tensors."""
+
+    def __init__(self, device, depth):
+        self.device, self.depth = device, depth
+        self.stream = torch.cuda.Stream(device)
+        self._staged = [torch.cuda.Event() for _ in range(depth)]
+        self._done = [torch.cuda.Event() for _ in range(depth)]
+        self._used = [False] * depth
+        self._last = None
+
+    def push(self, b, pairs):
+        """pairs: [(device result, device staging, pinned host)].  Called on the compute stream right after the forward."""
+        main = torch.cuda.current_stream(self.device)
+        if self._used[b]:
+            main.wait_event(self._done[b])  # the staging tensors' previous read-back (depth submits ago) has finished
+        for src, stage, _ in pairs:
+            stage.copy_(src, non_blocking=True)
+        self._staged[b].record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._staged[b])
+            for _, stage, host in pairs:
+                host.copy_(stage, non_blocking=True)
+            self._done[b].record(self.stream)
+        self._used[b] = True
+        self._last = self._done[b]
+
+    def fence(self):
+        """Make the current stream wait for every read-back queued so far (then synchronising it is enough)."""
+        if self._last is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._last)
+
+    def synchronize(self):
+        if self._last is not None:
+            self._last.synchronize()
 
 
 class HostScorer:
@@ -17,6 +56,7 @@ class HostScorer:
         self.device = torch.device(device)
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(self.device)
+        self._rb = _ReadBack(self.device, depth)
         self._bufs = None
         self._copied = [torch.cuda.Event() for _ in range(depth)]
         self._consumed = [torch.cuda.Event() for _ in range(depth)]
@@ -25,22 +65,34 @@ class HostScorer:
     def _ensure(self, q, r):
         key = (tuple(q.shape), tuple(r.shape))
         if self._bufs is None or self._bufs[0] != key:
+            self.synchronize()
             dev = self.device
             qs = [torch.empty(q.shape, dtype=torch.float32, device=dev) for _ in range(self.depth)]
             rs = [torch.empty(r.shape, dtype=torch.float32, device=dev) for _ in range(self.depth)]
             B, H, W = q.shape[0], 14 * (q.shape[-2] // 14), 14 * (q.shape[-1] // 14)
+            stage = [torch.empty(B, H, W, dtype=torch.float32, device=dev) for _ in range(self.depth)]
             outs = [torch.empty(B, H, W, dtype=torch.float32).pin_memory() for _ in range(self.depth)]
-            self._bufs = (key, qs, rs, outs)
+            self._bufs = (key, qs, rs, stage, outs)
+            self._rb = _ReadBack(self.device, self.depth)
             self._step = 0
         return self._bufs[1:]
 
     def h2d_bytes(self, q, r):
         return q.numel() * 4 + r.numel() * 4
 
+    def fence(self):
+        """The current stream waits for all queued read-backs."""
+        self._rb.fence()
+
+    def synchronize(self):
+        """Block the host until every returned host tensor is complete."""
+        self._rb.synchronize()
+
     def submit(self, q_host: torch.Tensor, r_host: torch.Tensor) -> torch.Tensor:
-        """Enqueue one batch (pinned fp32 host tensors).  Returns the pinned host tensor that will hold the
-        score maps once the current stream has been synchronised (valid until `depth` later submits)."""
-        qs, rs, outs = self._ensure(q_host, r_host)
+        """Enqueue one batch (pinned fp32 host tensors).  Returns the pinned host tensor that will hold the score maps
+        after ``synchronize()`` (or ``fence()`` + a synchronise of the current stream); it is reused `depth` submits
+        later."""
+        qs, rs, stage, outs = self._ensure(q_host, r_host)
         b = self._step % self.depth
         main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.copy_stream):
@@ -52,7 +104,7 @@ class HostScorer:
         main.wait_event(self._copied[b])
         score = self.net(qs[b], rs[b], False, 0, False)["score_map_ref_cross"]
         self._consumed[b].record(main)
-        outs[b].copy_(score, non_blocking=True)
+        self._rb.push(b, [(score, stage[b], outs[b])])
         self._step += 1
         return outs[b]
 
@@ -70,14 +122,23 @@ class HostPipeline:
         self.net, self.device, self.depth = net, torch.device(device), depth
         self.resize, self.vrange = resize_short_side, list(gray16_vrange)
         self.copy_stream = torch.cuda.Stream(self.device)
+        self._rb = _ReadBack(self.device, depth)
         self._bufs = None
         self._copied = [torch.cuda.Event() for _ in range(depth)]
         self._consumed = [torch.cuda.Event() for _ in range(depth)]
         self._step = 0
 
+    def fence(self):
+        self._rb.fence()
+
+    def synchronize(self):
+        self._rb.synchronize()
+
     def _ensure(self, q, r):
         key = (tuple(q.shape), tuple(r.shape))
         if self._bufs is None or self._bufs[0] != key:
+            self.synchronize()
+            self._rb = _ReadBack(self.device, self.depth)
             dev = self.device
             qs = [torch.empty(q.shape, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
             rs = [torch.empty(r.shape, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
@@ -86,6 +147,8 @@ class HostPipeline:
             H, W = 14 * (H1 // 14), 14 * (W1 // 14)
             means = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(self.depth)]
             maps = [torch.empty(B, H, W, dtype=torch.uint16).pin_memory() for _ in range(self.depth)]
+            self._stage = [(torch.empty(B, dtype=torch.float32, device=dev),
+                            torch.empty(B, H, W, dtype=torch.uint16, device=dev)) for _ in range(self.depth)]
             self._bufs = (key, qs, rs, means, maps)
             self._step = 0
         return self._bufs[1:]
@@ -99,7 +162,7 @@ class HostPipeline:
 
     def submit(self, q_host: torch.Tensor, r_host: torch.Tensor):
         """q_host (B,H,W,3), r_host (B,N,H,W,3) pinned uint8.  Returns (means, maps16) pinned host tensors, valid
-        once the current stream has been synchronised (until `depth` later submits)."""
+        after ``synchronize()`` (or ``fence()`` + a synchronise of the current stream) until `depth` later submits."""
         qs, rs, means, maps = self._ensure(q_host, r_host)
         b = self._step % self.depth
         main = torch.cuda.current_stream(self.device)
@@ -116,8 +179,8 @@ class HostPipeline:
         self._consumed[b].record(main)
         score = self.net(q, r.view(B, N, *r.shape[1:]), False, 0, False)["score_map_ref_cross"]
         out = self.imgproc.postprocess_scores(score, mean=True, gray16_vrange=self.vrange)
-        means[b].copy_(out["mean"], non_blocking=True)
-        maps[b].copy_(out["gray16"], non_blocking=True)
+        sm, sg = self._stage[b]
+        self._rb.push(b, [(out["mean"], sm, means[b]), (out["gray16"], sg, maps[b])])
         self._step += 1
         return means[b], maps[b]
 

@@ -126,8 +126,8 @@ int xs_gemm_bias_residual_ln(const void* A, int lda, const void* W, int ldw, con
                              const float* gamma, const float* beta, float eps, void* y, int ldy, int M, int N, int K,
                              int dtype, xs_stream_t stream);
 
-/* K6+K2 / K7+K2 with the LayerNorm FOLDED into the GEMM that consumes it (the default plan of the bf16 mode for large
- *     batches).  The same two reference steps as above (modeling_dinov2.py:367-386, 312-328, 203-234), split differently:
+/* K6+K2 / K7+K2 with the LayerNorm FOLDED into the GEMM that consumes it (opt-in plan, XS_FOLD_LN=1 in the host module:
+ *     measured slower than the LayerNorm kernels and less precise with outlier channels).  The same two reference steps as above (modeling_dinov2.py:367-386, 312-328, 203-234), split differently:
  *       producer:  h (fp32, in place) += A @ W^T + bias;  hb (bf16) = h;  stats[r] = (mean_r, rstd_r) of row r of h
  *       consumer:  out (bf16) = act( rstd_r * (hb @ Wf^T - mean_r * c1) + c0 )
  *     with Wf = bf16(gamma * W) (LayerNorm weight folded into the next Linear's weight), c1[n] = sum_k Wf[n,k] and
