@@ -321,6 +321,10 @@ def test_flash_attn_f32(B, H, Lq, Lk, d, slot, nsplit, shared):
     (3, 8, 200, 700, 48, 1, True, 1.0),      # shared reference K/V
     (2, 3, 1370, 700, 64, 1, False, 1.0),    # odd tile count AND odd head count (pair layout: mixed units, a lone tile)
     (2, 5, 300, 900, 48, 2, False, 1.0),     # the same with split-KV
+    (1, 1, 1, 1, 64, 1, False, 1.0),         # one query, one key
+    (2, 3, 5, 77, 48, 1, False, 1.0),        # a few rows, less than one key block
+    (1, 8, 129, 127, 48, 1, False, 1.0),     # one row into the second tile, one key short of a block
+    (3, 1, 257, 385, 64, 1, True, 1.0),      # single head: every odd tile is a lone unit
 ])
 def test_flash_attn_bf16_tc(B, H, Lq, Lk, d, nsplit, shared, qscale, layout):
     o, ref, lse, lse_ref = run_attn(DT_BF16, B, H, Lq, Lk, d, 64, nsplit, shared, qscale=qscale)
