@@ -9,7 +9,7 @@ shape = sys.argv[1] if len(sys.argv) > 1 else "dino"
 I, H, T, Lk, d = {"dino": (48, 6, 1370, 1370, 64), "dino192": (192, 6, 1370, 1370, 64), "dec": (32, 8, 1369, 6845, 48),
                   "dsa": (32, 8, 1369, 1369, 48), "cfg5": (17, 6, 5477, 5477, 64)}[shape]
 SCALE1 = os.environ.get("SCALE1", "1") == "1"
-LAYOUT = int(os.environ.get("LAYOUT", "0"))
+LAYOUT = int(os.environ.get("LAYOUT", "1"))
 if hasattr(_lib.load(), "xs_attn_set_layout"):
     _lib.load().xs_attn_set_layout(LAYOUT)
 torch.manual_seed(0)
