@@ -368,6 +368,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from crossscore_b200.runner import bind_to_gpu_numa
+    # multi-GPU: before any pinned allocation, so that host buffers live on the GPU's own socket (N = 1 keeps every core
+    # for the CPU baseline leg)
+    numa_cpus = bind_to_gpu_numa(local) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -522,7 +526,8 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "maps/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": scorer.h2d_bytes(qh, rh), "d2h_bytes_per_step": int(host_out.numel() * 4)},
+                "h2d_bytes_per_step": scorer.h2d_bytes(qh, rh), "d2h_bytes_per_step": int(host_out.numel() * 4),
+                "cpus_bound_to_gpu_numa_node": numa_cpus},
         "pipeline": pipeline,
         "latency_cfg1": latency,
         "gpu_launches": launches,

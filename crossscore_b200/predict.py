@@ -314,6 +314,8 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
         import torch.distributed as dist
+        from .runner import bind_to_gpu_numa
+        bind_to_gpu_numa(local)  # decode threads and pinned buffers on the GPU's own socket
         dist.init_process_group("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
