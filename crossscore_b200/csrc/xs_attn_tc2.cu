@@ -1,7 +1,9 @@
-// Flash attention, second layout ("pair" kernel): ONE CTA per SM works on TWO adjacent 128-row query tiles of a
-// (batch, head) that share every K/V tile, in 128-key blocks.  O = softmax(Q K^T * scale) V, same contract as
-// xs_attn_tc.cu (which keeps the 64-key / two-CTAs-per-SM layout and remains the fallback for shapes this one
-// does not take).
+// Flash attention, "pair" layout (the default, xs_attn_set_layout(1)): ONE CTA per SM works on TWO 128-row query tiles
+// at a time, in 128-key blocks -- normally two adjacent tiles of a (batch, head), which share every K/V tile; when the
+// tile count is odd, the last tiles of two different heads, each with its own K/V stages (struct Unit below).
+// O = softmax(Q K^T * scale) V, same contract as xs_attn_tc.cu (which keeps the 64-key / two-CTAs-per-SM layout,
+// selectable with xs_attn_set_layout(0)); reference call sites: modeling_dinov2.py:203-234 (DINOv2 SDPA),
+// torch/nn/functional.py:6630-6692 via model/customised_transformer/transformer.py:182-205 (decoder).
 //
 // Why: the 64-key kernel is bounded by issue slots and the MUFU together (ncu: issue 58 %, MUFU 67 %, tensor 42 %), and
 // 28 % of its instructions are per-block overhead -- three control warps (TMA, PV issuer, QK issuer) at ~135
@@ -13,14 +15,15 @@
 // 640 threads:
 //   warps 0-7   softmax of query tile A, warps 8-15 of tile B: warp w owns 16 rows (TMEM lane quarter w % 4, lower / upper
 //               half by (w / 4) % 2), tcgen05.ld.16x256b fragments, 64 logits per thread and block in two halves
-//   warp 16     TMA producer: Q_A, Q_B per unit; K / V 128-key tiles through a 4-stage ring
+//   warp 16     TMA producer: Q_A, Q_B per unit; K / V 128-key tiles through a 5-stage ring
 //   warp 17     PV issuer  (O_t += P_t V, 8 K-steps per block and tile; P read from TMEM)
 //   warp 18     QK issuer  (S_t = Q_t K^T, N = 128)
 //   warp 19     TMEM allocator
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 // S is single-buffered per tile but P has its own columns: a softmax warp releases S_t as soon as both halves of the
 // block are in registers (s_free), so QK_{j+1} of that tile runs under the exponentials of block j, and PV_j reads P_t
-// while S_t is already being overwritten.  The two tiles run the same chain half a phase apart.
+// while S_t is already being overwritten.  Both tiles run the same chain, in phase (a forced offset measured slower:
+// profiles/r2_attn_experiments.txt item 12).
 // Softmax arithmetic, redo pass, masking, split-KV outputs: as in xs_attn_tc.cu (max-free first pass, online-softmax
 // redo of tiles whose row sums leave [2^-80, 2^100]).
 #include "xs_common.cuh"
