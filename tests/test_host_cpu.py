@@ -118,3 +118,22 @@ def test_attention_key_split_heuristic():
         n = attn_kv_splits(tiles, nblk)
         per = -(-nblk // n)
         assert 1 <= n <= 8 and (n - 1) * per < nblk     # every range owns at least one key block
+
+
+def test_numa_binding_helper_is_a_noop_without_nvml():
+    """runner.bind_to_gpu_numa never raises: no GPU / no NVML here -> 0 CPUs bound and the affinity mask untouched."""
+    import os
+    from crossscore_b200.runner import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) == 0 or os.sched_getaffinity(0) <= before
+    os.environ["XS_NUMA_BIND"] = "0"
+    try:
+        assert bind_to_gpu_numa(0) == 0
+    finally:
+        del os.environ["XS_NUMA_BIND"]
+    assert os.sched_getaffinity(0) <= before
+
+
+def test_folded_layernorm_row_threshold():
+    from crossscore_b200.engine import Engine
+    assert not Engine.fold_ln_rows(6 * 1370) and Engine.fold_ln_rows(14 * 1370) and Engine.fold_ln_rows(192 * 1370)
