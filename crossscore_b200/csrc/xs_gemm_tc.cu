@@ -58,7 +58,8 @@ struct GemmSmem {
   static constexpr uint32_t WARP_STAGE_BYTES = 32 * 32 * ((OUT == 1 || OUT == 2) ? 4 : 2);
   static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr uint32_t B_BYTES = (CTA2 ? BN / 2 : BN) * GEMM_BK * 2;  // a CTA pair splits the W tile rows
-  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4;
+  // jigsaw epilogue: the fp32 score tile + one 64-bit output offset per token of the tile
+  static constexpr uint32_t STAGING_BYTES = (EPI == EPI_STORE) ? 8 * 2 * WARP_STAGE_BYTES : GEMM_BM * JIG_LD * 4 + GEMM_BM * 8;
   static constexpr int A_SLOTS = (CTA2 == 2) ? GEMM_KB_MAX : STAGES;  // A-stationary: one slot per k-block of the m-block
   static constexpr uint32_t OFF_A = 0;
   static constexpr uint32_t OFF_B = OFF_A + A_SLOTS * A_BYTES;
@@ -581,30 +582,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int k = c * 32 + j;
             if (k < 196) {
               const float z = __uint_as_float(v[j]) + __ldg(bias + k);
-              float s = jp.use_tanh ? tanhf(z) : 1.0f / (1.0f + expf(-z));
+              float s = jp.use_tanh ? tanhf(z) : __fdividef(1.0f, 1.0f + __expf(-z));
               if (jp.power != 1.0f) s = powf(s, jp.power);
               stile[row * JIG_LD + k] = s;
             }
           }
         }
         (void)LAST;
-        named_bar_sync(1, EPI_THREADS);
+        // where each token's 14 x 14 patch starts in the score map (utils/misc/image.py:8-21): the divisions once per token
         const int m0 = m_blk * GEMM_BM;
         const int rows_valid = min(GEMM_BM, M - m0);
-        // (i, token, j) order: consecutive tokens of one grid row are contiguous in the image row
-        for (int e = epi_tid; e < 14 * GEMM_BM * 14; e += EPI_THREADS) {
-          const int i = e / (GEMM_BM * 14);
-          const int rem = e - i * (GEMM_BM * 14);
-          const int tt = rem / 14;
-          const int j = rem - tt * 14;
+        long long* tok_off = reinterpret_cast<long long*>(stile + GEMM_BM * JIG_LD);
+        if (epi_tid < rows_valid) {
+          const int t = m0 + epi_tid;
+          const int b = t / jp.P;
+          const int p = t - b * jp.P;
+          const int r = p / jp.pw;
+          const int cc = p - r * jp.pw;
+          tok_off[epi_tid] = static_cast<long long>(b) * jp.HWout + static_cast<long long>(14 * r) * jp.Wout + 14 * cc;
+        }
+        named_bar_sync(1, EPI_THREADS);
+        // one (patch row i, token) pair per thread and step: 14 contiguous floats as seven 8-byte stores (every offset is
+        // even: Wout = 14 pw).  Consecutive threads take consecutive tokens, i.e. consecutive 56-byte pieces of an image row.
+        for (int e = epi_tid; e < 14 * GEMM_BM; e += EPI_THREADS) {
+          const int i = e / GEMM_BM;
+          const int tt = e - i * GEMM_BM;
           if (tt < rows_valid) {
-            const int t = m0 + tt;
-            const int b = t / jp.P;
-            const int p = t - b * jp.P;
-            const int r = p / jp.pw;
-            const int cc = p - r * jp.pw;
-            jp.score[static_cast<size_t>(b) * jp.HWout + static_cast<size_t>(14 * r + i) * jp.Wout + 14 * cc + j] =
-                stile[tt * JIG_LD + i * 14 + j];
+            const float* src = stile + tt * JIG_LD + i * 14;
+            float2* dst = reinterpret_cast<float2*>(jp.score + tok_off[tt] + static_cast<long long>(i) * jp.Wout);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) dst[j] = make_float2(src[2 * j], src[2 * j + 1]);
           }
         }
         named_bar_sync(1, EPI_THREADS);  // staging tile is reused by the next tile
@@ -895,6 +902,7 @@ int head_jigsaw_tc(const void* A, int lda, const void* W, int ldw, const float* 
   const int al = in_tf32 ? 4 : 8;
   XS_CHECK_ARG(B > 0 && ph > 0 && pw > 0, "head_jigsaw: empty problem");
   XS_CHECK_ARG((K % al) == 0 && (lda % al) == 0 && (ldw % al) == 0, "head_jigsaw: K/lda/ldw must be 16-byte multiples");
+  XS_CHECK_ARG((reinterpret_cast<uintptr_t>(score) & 7) == 0, "head_jigsaw: the score map must be 8-byte aligned");
   JigsawParams jp;
   jp.score = score;
   jp.P = ph * pw;
