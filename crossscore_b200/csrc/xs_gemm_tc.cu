@@ -107,7 +107,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const float* __restrict__ bias, int M, int N, int K, JigsawParams jp, LnParams lnp) {
   using L = GemmSmem<BN, STAGES, EPI, CTA2, OUT, LNF>;
   static_assert(!LNF || (OUT == OUT_F32_ADD && EPI == EPI_STORE && BN == 192), "LN fusion: residual epilogue only");
-  static_assert(!CTA2 || (IN == IN_BF16 && EPI == EPI_STORE), "CTA pairs: bf16 store epilogue only");
+  static_assert(!CTA2 || EPI == EPI_STORE, "CTA pairs: store epilogue only");
+  static_assert(CTA2 != 2 || IN == IN_BF16, "A-stationary pairs: bf16 operands (K <= 384 must fit six 64-element k-blocks)");
   constexpr int NC = CTA2 ? 2 : 1;                       // CTAs per tile
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader
   const int worker = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
@@ -233,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (converged warp, uniform operands, one elected lane issues) =========
     constexpr uint32_t idesc =
-        (IN == IN_TF32) ? umma_idesc_tf32(GEMM_BM, BN) : umma_idesc_bf16(NC * GEMM_BM, BN, 0, 0);
+        (IN == IN_TF32) ? umma_idesc_tf32(NC * GEMM_BM, BN) : umma_idesc_bf16(NC * GEMM_BM, BN, 0, 0);
     const uint32_t tb = warp_uniform(tmem_base);
     const uint32_t a_lo0 = umma_desc_lo(smem_u32(smA), 16);
     const uint32_t b_lo0 = umma_desc_lo(smem_u32(smB), 16);
@@ -279,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (CTA2) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss_lh_pair(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss_lh_pair<IN == IN_TF32>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             tc_commit_pair(&empty_bar[stage]);  // frees the slot in BOTH CTAs
             if (kb == num_k - 1) tc_commit_pair(&tmem_full[acc_stage]);
           } else {
@@ -804,6 +805,12 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
     return launch_gemm<256, 3, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32>(XS_GEMM_ARGS);
   }
   if (in_tf32 && out_f32) {
+    // CTA pairs once there are enough 256-row tiles for every pair of SMs (patch embedding and the decoder GEMMs of a
+    // full batch): each CTA stages half of the W tile, which is what bounds these fp32-operand GEMMs (L2 -> SM).
+    // In-run A/B: patch embedding 0.68 -> 0.61 ms per step, decoder GEMMs 0.59 -> 0.58 (profiles/r2_experiments.txt).
+    const int num_m2 = (M + 255) / 256;
+    if (use192 && num_m2 * (N / 192) >= num_sms() / 2)
+      return dispatch_act<192, 5, IN_TF32, OUT_F32, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
     if (use192) return dispatch_act<192, 4, IN_TF32, OUT_F32>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
     return dispatch_act<256, 3, IN_TF32, OUT_F32>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
   }

@@ -98,7 +98,9 @@ def test_gemm_bf16_tc(M, N, K, act):
     (2738, 384, 588, ACT_NONE, False),   # patch embedding: K tail block zero-filled by TMA
     (1369, 1536, 384, ACT_NONE, True),   # decoder self-attention in-proj -> bf16 q|k|v
     (1369, 512, 384, ACT_NONE, True),    # cross-attention q-proj
-    (30000, 384, 384, ACT_NONE, False),  # persistent loop
+    (30000, 384, 384, ACT_NONE, False),  # persistent loop; CTA pairs (cta_group::2, kind::tf32)
+    (43808, 384, 588, ACT_RELU, False),  # CTA pairs, patch-embedding K (zero-filled tail block), ragged M
+    (19001, 1152, 384, ACT_LEAKY, False),  # CTA pairs, six n-tiles, peer CTA rows out of range
 ])
 def test_gemm_tf32_tc(M, N, K, act, out_bf16):
     A, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05), rnd(N, seed=3)
