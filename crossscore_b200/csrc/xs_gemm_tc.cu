@@ -722,6 +722,21 @@ static int dispatch_act(const void* A, int lda, const void* W, int ldw, const fl
   return -1;
 }
 
+// A-stationary CTA pairs walk whole 256-row blocks: with num_m2 blocks on SMs/2 pairs the last wave may be nearly empty
+// (172 blocks on 74 pairs = 2.3 waves -> 3).  Below this wave efficiency the streaming pair kernel, whose unit is one
+// 256 x BN tile, is used instead.  Measured (profiles/r2_experiments.txt): at 43 840 rows (32 query images, cfg 3) the
+// streaming pairs win by 19 % (q|k|v), 26 % (fc1), 12 % (N = 384); at 65 000 rows (efficiency 0.86) still by 7-12 %; at the
+// headline's 263 040 rows (0.99) the A-stationary form is the faster one.
+#ifndef XS_ASTAT_MIN_EFF
+#define XS_ASTAT_MIN_EFF 0.92f
+#endif
+static bool astat_pays(int num_m2) {
+  const int pairs = num_sms() / 2;
+  if (num_m2 < pairs) return false;
+  const int waves = (num_m2 + pairs - 1) / pairs;
+  return static_cast<float>(num_m2) >= XS_ASTAT_MIN_EFF * static_cast<float>(waves * pairs);
+}
+
 // Tensor-core GEMM entry used by xs_api.cu.  in_tf32: A/W are fp32 (TF32 multiply), else bf16.
 // out_f32: 0 bf16 output, 1 fp32 output, 2 fp32 output accumulated in place (out += ...), 3 fp16 output.
 // N must be a multiple of 192 or 256; row pitches must be multiples of 16 bytes.
@@ -771,12 +786,12 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
     const bool fits = num_m2 * (N / bn) >= num_sms() / 2;
     const bool pair = fits && K >= 1024;
     // K <= 384 (qkv, proj, fc1): A-stationary pairs once every pair of SMs has a 256-row block of its own
-    const bool astat = K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2;
+    const bool astat = K <= GEMM_KB_MAX * GEMM_BK && astat_pays(num_m2);
     if (astat) {
       if (use192) return dispatch_act<192, 8, IN_BF16, OUT_BF16, 2>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
       return dispatch_act<256, 6, IN_BF16, OUT_BF16, 2>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
     }
-    if (pair) {
+    if (pair || (fits && num_m2 >= num_sms() / 2)) {
       if (use192) return dispatch_act<192, 6, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
       return dispatch_act<256, 6, IN_BF16, OUT_BF16, 1>(A, lda, W, ldw, bias, out, ldc, M, N, K, act, stream);
     }
@@ -792,9 +807,9 @@ int gemm_tc(const void* A, int lda, const void* W, int ldw, const float* bias, v
     XS_CHECK_ARG(use192, "gemm: residual accumulate needs N %% 192 == 0 (N=%d)", N);
     const int num_m2 = (M + 255) / 256;
     const bool fits = num_m2 * (N / 192) >= num_sms() / 2;
-    if (K <= GEMM_KB_MAX * GEMM_BK && num_m2 >= num_sms() / 2)
+    if (K <= GEMM_KB_MAX * GEMM_BK && astat_pays(num_m2))
       return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 2>(XS_GEMM_ARGS);
-    if (fits && K >= 1024)
+    if (fits && (K >= 1024 || num_m2 >= num_sms() / 2))
       return launch_gemm<192, 5, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD, 1>(XS_GEMM_ARGS);
     return launch_gemm<192, 4, EPI_STORE, ACT_NONE, IN_BF16, OUT_F32_ADD>(XS_GEMM_ARGS);
   }

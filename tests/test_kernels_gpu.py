@@ -69,9 +69,12 @@ def test_gemm_f32(M, N, K, act):
     (777, 384, 1536, ACT_NONE),     # fc2 K
     (1369, 2048, 384, ACT_NONE),    # BN=256
     (1369, 512, 384, ACT_RELU),
-    (40000, 384, 384, ACT_LEAKY),   # many tiles per CTA (persistent loop, phase wrap); A-stationary CTA pairs, BN=192
-    (19999, 1152, 384, ACT_NONE),   # A-stationary CTA pairs, 6 n-tiles per row block, ragged M (peer CTA rows out of range)
-    (20000, 1536, 384, ACT_GELU),   # A-stationary CTA pairs, BN=256
+    (37800, 384, 384, ACT_LEAKY),   # A-stationary CTA pairs (148 row blocks = two full waves), BN=192, ragged M
+    (18900, 1152, 384, ACT_NONE),   # A-stationary CTA pairs, 6 n-tiles per row block, ragged M (peer CTA rows out of range)
+    (37801, 1536, 384, ACT_GELU),   # A-stationary CTA pairs, BN=256
+    (40000, 384, 384, ACT_LEAKY),   # 157 row blocks = 2.1 waves: streaming CTA pairs at K = 384 (many tiles per CTA, phase wrap)
+    (19999, 1152, 384, ACT_NONE),   # streaming CTA pairs, short K, ragged M
+    (20000, 1536, 384, ACT_GELU),   # streaming CTA pairs, short K, BN=256
     (19999, 384, 1536, ACT_NONE),   # streaming CTA pairs (cta_group::2), long K
     (18945, 512, 1024, ACT_RELU),   # streaming CTA pairs, BN=256
 ])
@@ -131,7 +134,8 @@ def test_gemm_bf16_in_f32_out():
 @pytest.mark.parametrize("M,N,K", [
     (128, 384, 384),      # single CTA per tile
     (1000, 384, 1536),    # single CTA, long K, ragged M
-    (40001, 384, 384),    # A-stationary CTA pairs (proj), ragged M: the reduce-store clips the tail rows
+    (37801, 384, 384),    # A-stationary CTA pairs (proj), two full waves, ragged M: the store clips the tail rows
+    (40001, 384, 384),    # 2.1 waves of row blocks: streaming CTA pairs at K = 384
     (39999, 384, 1536),   # streaming CTA pairs (fc2)
 ])
 def test_gemm_bias_residual(M, N, K):
