@@ -19,9 +19,11 @@ def bind_to_gpu_numa(device_index: int) -> int:
     """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node / PCIe root).
 
     One process per GPU: pinned host buffers are then allocated on (first touched from) the socket the GPU hangs off, so
-    the H2D copies of eight ranks do not all cross the inter-socket link.  Returns the number of CPUs bound to; 0 when
-    NVML or the affinity call is unavailable, the mask is empty or XS_NUMA_BIND=0 (then nothing changes)."""
-    if os.environ.get("XS_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+    the H2D copies of eight ranks do not all cross the inter-socket link.  Opt-in (XS_NUMA_BIND=1): on this pool's
+    single-socket VMs it changes nothing for the copies (measured) and the narrower CPU mask is not free for NCCL's helper
+    threads.  Returns the number of CPUs bound to; 0 when not enabled, when NVML or the affinity call is unavailable or
+    the mask is empty (then nothing changes)."""
+    if os.environ.get("XS_NUMA_BIND", "0") != "1" or not hasattr(os, "sched_setaffinity"):
         return 0
     try:
         import pynvml

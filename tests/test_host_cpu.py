@@ -125,10 +125,10 @@ def test_numa_binding_helper_is_a_noop_without_nvml():
     import os
     from crossscore_b200.runner import bind_to_gpu_numa
     before = os.sched_getaffinity(0)
-    assert bind_to_gpu_numa(0) == 0 or os.sched_getaffinity(0) <= before
-    os.environ["XS_NUMA_BIND"] = "0"
+    assert bind_to_gpu_numa(0) == 0                    # opt-in: off by default
+    os.environ["XS_NUMA_BIND"] = "1"
     try:
-        assert bind_to_gpu_numa(0) == 0
+        assert bind_to_gpu_numa(0) == 0 or os.sched_getaffinity(0) <= before
     finally:
         del os.environ["XS_NUMA_BIND"]
     assert os.sched_getaffinity(0) <= before
