@@ -613,3 +613,18 @@ def test_gemm_bias_residual_rejects_bad_shapes():
     b, h = rnd(200), rnd(128, 200)
     with pytest.raises(_lib.XsError):      # N must be a multiple of 192
         call("xs_gemm_bias_residual", P(A), 384, P(W), 384, P(b), P(h), 200, 128, 200, 384, DT_BF16, st())
+
+
+def test_flash_attn_bf16_tc_redo_in_mixed_units(layout):
+    """Odd tile count and odd head count: in the pair layout the last tiles of heads 0 and 1 share a unit (each with its
+    own K/V stream) and head 2's last tile is alone in one.  Only head 1 carries a ramp that overflows the max-free pass,
+    so redone and first-pass tiles meet inside one mixed unit, and a lone-tile unit runs next to them."""
+    B, H, Lq, Lk, d = 2, 3, 384, 1000, 64
+    j = torch.arange(Lk, dtype=torch.float32)
+    q, k, v = _ramp_inputs(B, H, Lq, Lk, d, j * 0.0)
+    k.view(B, Lk, H, 64)[:, :, 1, 0] = (j * (300.0 / Lk)).to(DEV).to(torch.bfloat16)[None, :]   # head 1 only
+    o, ref, lse, lse_ref = _attn_case(q, k, v, 1.0, d)
+    assert torch.isfinite(o).all()
+    err = (o - ref).abs()
+    assert err.max() < 0.03 and err.mean() < 3e-3, (err.max().item(), err.mean().item())
+    assert (lse - lse_ref).abs().max() < 0.05
